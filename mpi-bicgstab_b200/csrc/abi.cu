@@ -1,0 +1,142 @@
+// abi.cu -- the extern "C" surface of libbicgstab_b200.so (include/bicgstab_b200.h).
+// Part 1: the reference's own entry points (solver.h:10-13, matrix.h:51) on host pointers.
+// Part 2: bicg_* extensions.
+#include "engine.hpp"
+
+#include <cmath>
+#include <cstring>
+
+using namespace bicg;
+
+static_assert(sizeof(CSR_Matrix) == 40, "CSR_Matrix layout must match matrix.h:19-26");
+static_assert(offsetof(CSR_Matrix, col) == 8 && offsetof(CSR_Matrix, ptr) == 16 && offsetof(CSR_Matrix, nz) == 24 &&
+              offsetof(CSR_Matrix, rows) == 28 && offsetof(CSR_Matrix, cols) == 32, "CSR_Matrix layout");
+static_assert(sizeof(INFO_Matrix) == 32, "INFO_Matrix layout must match matrix.h:28-33");
+static_assert(offsetof(INFO_Matrix, code) == 12 && offsetof(INFO_Matrix, recvcounts) == 16 &&
+              offsetof(INFO_Matrix, displs) == 24, "INFO_Matrix layout");
+
+namespace {
+
+int run_reference_entry(int method, CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x, double *r, int krr, int nrr)
+{
+    if (info->cols != info->rows) {                      // solver.c:43-46
+        printf("Error: matrix is not square.\n");
+        exit(1);
+    }
+    Context &c = ctx();
+    c.ensure();
+    bool fresh = false;
+    bicg_matrix *m = matrix_get_cached(D, O, info, &fresh);
+    bicg_stats st{};
+    solve(m, method, x, r, krr, nrr, 0, &st);
+    st.upload_ms = fresh ? m->upload_ms : 0.0;
+    st.h2d_bytes += fresh ? m->upload_bytes : 0;
+    c.last_stats = st;
+    print_reference_lines(st, c.last_hist);
+    if (!c.cfg.cache) matrix_destroy(m);
+    return st.iters;
+}
+
+} // namespace
+
+extern "C" {
+
+int bicgstab(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_loc, double *r_loc)
+{
+    return run_reference_entry(BICG_METHOD_BICGSTAB, D, O, info, x_loc, r_loc, 0, 0);
+}
+int ca_bicgstab(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_loc, double *r_loc)
+{
+    return run_reference_entry(BICG_METHOD_CA, D, O, info, x_loc, r_loc, 0, 0);
+}
+int pipe_bicgstab(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_loc, double *r_loc)
+{
+    return run_reference_entry(BICG_METHOD_PIPE, D, O, info, x_loc, r_loc, 0, 0);
+}
+int pipe_bicgstab_rr(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_loc, double *r_loc, int krr, int nrr)
+{
+    return run_reference_entry(BICG_METHOD_PIPE_RR, D, O, info, x_loc, r_loc, krr, nrr);
+}
+
+void MPI_csr_spmv_ovlap(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_loc, double *x, double *y_loc)
+{
+    Context &c = ctx();
+    c.ensure();
+    bicg_matrix *m = matrix_get_cached(D, O, info, nullptr);
+    if (x && m->world > 1) memcpy(x + info->displs[m->rank], x_loc, (size_t)m->n_loc * sizeof(double));
+    spmv_host(m, x_loc, y_loc, x);
+    if (!c.cfg.cache) matrix_destroy(m);
+}
+
+// ---- Part 2 ------------------------------------------------------------------------------------------
+
+int bicg_abi_version(void) { return BICG_ABI_VERSION; }
+
+int bicg_set_option(const char *key, const char *value) { return set_option(ctx().cfg, key, value); }
+
+int bicg_comm_init(int rank, int world, bicg_allgather_fn allgather, void *user)
+{
+    if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world) return -1;
+    Context &c = ctx();
+    c.rank = rank; c.world = world; c.allgather = allgather; c.allgather_ctx = user;
+    return 0;
+}
+void bicg_comm_finalize(void)
+{
+    Context &c = ctx();
+    std::vector<bicg_matrix *> ms;
+    for (auto &kv : c.cache) ms.push_back(kv.second);
+    for (bicg_matrix *m : ms) matrix_destroy(m);
+    c.cache.clear();
+    c.rank = 0; c.world = 1; c.allgather = nullptr; c.allgather_ctx = nullptr;
+}
+int bicg_comm_rank(void) { return ctx().rank; }
+int bicg_comm_world(void) { return ctx().world; }
+
+bicg_matrix *bicg_matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info)
+{
+    return matrix_create(diag, offd, info);
+}
+void bicg_matrix_destroy(bicg_matrix *m) { matrix_destroy(m); }
+void bicg_matrix_invalidate(const CSR_Matrix *diag)
+{
+    Context &c = ctx();
+    if (!diag) return;
+    const void *key = diag->val ? (const void *)diag->val : (const void *)diag;
+    auto it = c.cache.find(key);
+    if (it == c.cache.end()) return;
+    bicg_matrix *m = it->second;
+    c.cache.erase(it);
+    if (m->world == 1) matrix_destroy(m);       // with peers, destruction is collective: leave it to bicg_comm_finalize
+    else c.cache[(const void *)m] = m;
+}
+
+int bicg_solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, int device_vectors, bicg_stats *stats)
+{
+    return solve(m, method, x, r, krr, nrr, device_vectors, stats);
+}
+int bicg_spmv(bicg_matrix *m, const double *x_loc, double *y_loc) { return spmv_host(m, x_loc, y_loc, nullptr); }
+int bicg_spmv_time(bicg_matrix *m, int reps, double *ms, double *bytes) { return spmv_time(m, reps, ms, bytes); }
+
+int bicg_last_history(double *out, int cap)
+{
+    Context &c = ctx();
+    const int n = (int)c.last_hist.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = c.last_hist[(size_t)i];
+    return n;
+}
+const bicg_stats *bicg_last_stats(void) { return &ctx().last_stats; }
+
+void *bicg_stream(void) { Context &c = ctx(); c.ensure(); return (void *)c.stream; }
+int bicg_device(void) { Context &c = ctx(); c.ensure(); return c.device; }
+void bicg_synchronize(void) { Context &c = ctx(); c.ensure(); BICG_CUDA(cudaStreamSynchronize(c.stream)); }
+void *bicg_host_alloc(size_t bytes)
+{
+    Context &c = ctx(); c.ensure();
+    void *p = nullptr;
+    BICG_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    return p;
+}
+void bicg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"

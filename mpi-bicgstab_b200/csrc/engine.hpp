@@ -1,0 +1,154 @@
+// engine.hpp -- host-side runtime of libbicgstab_b200: process context, device-resident matrix, solver driver.
+#pragma once
+#include "bicgstab_b200.h"
+#include "dev.cuh"
+#include "plan.hpp"
+#include "spmv.cuh"
+#include "vec.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace bicg {
+
+[[noreturn]] void fatal(const char *fmt, ...);
+#define BICG_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            ::bicg::fatal("bicgstab_b200: CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, \
+                          __LINE__, cudaGetErrorString(e_));                                          \
+    } while (0)
+
+struct Config {
+    double tol = 1.0e-15;        // solver.c:3
+    int max_iter = 1000;         // solver.c:4
+    int out_iter = 100;          // solver.c:9
+    int quiet = 0;
+    int spmv_kind = -1;          // -1 auto, 0 tma, 1 rowsplit
+    int spmv_lanes = 0;          // 0 choose
+    int spmv_threads = 0;
+    int spmv_stages = 0;
+    int spmv_ctas = 0;           // CTAs per SM (0 choose)
+    int autotune = 1;
+    int graph = 1;
+    int unroll = 10;
+    int cache = 1;
+    int device = -1;
+    int halo_gap = 64;
+    int verbose = 0;
+};
+
+struct Context {
+    bool ready = false;
+    Config cfg;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // job
+    int rank = 0, world = 1;
+    bicg_allgather_fn allgather = nullptr;
+    void *allgather_ctx = nullptr;
+    // results of the last solve
+    std::vector<double> last_hist;
+    bicg_stats last_stats{};
+    // host-pointer keyed cache of uploaded matrices
+    std::map<const void *, bicg_matrix *> cache;
+    // pinned scratch
+    int *h_flags = nullptr;      // ring of {k, max_iter, done, converged}
+    // profiling of individual launches
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_class;
+    int launches = 0;
+
+    void ensure();               // lazy device init; fails loudly if there is no usable GPU
+    void host_allgather(const void *send, void *recv, size_t bytes);
+};
+Context &ctx();
+void load_config_from_env(Config &c);
+int  set_option(Config &c, const char *key, const char *value);
+
+enum VecId { V_X = 0, V_R, V_RH, V_P, V_S, V_Y, V_W, V_V, V_T, V_B, V_AX, V_COUNT };
+// V_Y doubles as z (the CA / pipelined variants call the same storage z)
+constexpr int V_Z = V_Y;
+
+struct SpmvPlan {
+    int kind = 0, lanes = 1, threads = 256, stages = 3, cap = 0, grid = 0, ctas_per_sm = 1;
+    size_t smem = 0;
+    int ntiles = 0;
+    int *d_tile_row = nullptr;
+    unsigned *d_tile_nz = nullptr;
+    double ms = 0.0;             // measured time of one launch (autotune) or 0
+};
+
+} // namespace bicg
+
+// the opaque handle of the C ABI
+struct bicg_matrix {
+    int rank = 0, world = 1;
+    int n_loc = 0, n_glob = 0;
+    size_t nnz = 0;              // entries of this rank's rows (diag + offd)
+    unsigned max_row = 0;
+    double mean_row = 0.0;
+    // device CSR over the extended local column space
+    double *d_val = nullptr;
+    unsigned *d_col = nullptr;
+    unsigned *d_ptr = nullptr;
+    bicg::SpmvPlan plan;
+    // ghost layout
+    int ghost_off = 0;           // first ghost column index = roundup(n_loc, 16)
+    int n_ghost = 0;
+    long long vstride = 0;       // doubles between consecutive arena vectors
+    std::vector<int> recv_runs;  // quadruples (first_col, len, owner, ghost_idx)
+    // arena (one cudaMalloc, IPC-shared with the peers)
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    double *vec_base = nullptr;
+    bicg::Scalars *d_sc = nullptr;
+    double *d_partials = nullptr;
+    double *d_hist = nullptr;
+    double *hist_extra = nullptr;   // replaces the arena slot when BICG_MAX_ITER grows
+    int hist_cap = 0;
+    bicg::Mailbox *d_mail = nullptr;
+    bicg::HaloFlag *d_hflag = nullptr;
+    bicg::CommDev comm{};
+    // peers
+    void *peer_base[bicg::MAX_RANKS] = {};
+    long long peer_vec_off[bicg::MAX_RANKS] = {}, peer_vstride[bicg::MAX_RANKS] = {}, peer_ghost_off[bicg::MAX_RANKS] = {};
+    int npush = 0;                                   // peers this rank sends to
+    int push_peer[bicg::MAX_RANKS - 1] = {};
+    bicg::PushRun *d_push_runs[bicg::MAX_RANKS - 1] = {};
+    int push_nruns[bicg::MAX_RANKS - 1] = {};
+    // fused-vector launch shape
+    int vgrid = 0, vchunk = 0;
+    // captured iteration batches, per method
+    cudaGraphExec_t graph[4] = {};
+    int graph_unroll[4] = {};
+    // cache key
+    const void *host_key = nullptr;
+    double upload_ms = 0.0;
+    uint64_t upload_bytes = 0;
+
+    double *vec(int id) const { return vec_base + (long long)id * vstride; }
+};
+
+namespace bicg {
+
+// matrix.cu
+bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info);
+void matrix_destroy(bicg_matrix *m);
+bicg_matrix *matrix_get_cached(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, bool *fresh);
+// solve.cu
+int  solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, int device_vectors, bicg_stats *st);
+int  spmv_host(bicg_matrix *m, const double *x_loc, double *y_loc, double *x_full_or_null);
+int  spmv_time(bicg_matrix *m, int reps, double *ms, double *bytes);
+void print_reference_lines(const bicg_stats &st, const std::vector<double> &hist);
+// helpers shared by matrix.cu / solve.cu
+SpmvArgs make_spmv_args(const bicg_matrix *m, const SpmvPlan &p, int x_id, int y_id);
+void launch_spmv_plan(const bicg_matrix *m, const SpmvPlan &p, const SpmvArgs &a, int prof_class = 0);
+
+} // namespace bicg

@@ -1,0 +1,513 @@
+// matrix.cu -- process context, configuration, and the device-resident matrix:
+//   * merge of the reference's diag / offd blocks (matrix.c:380-392) into one CSR over the extended local
+//     column space [own columns | ghost columns], upload into padded HBM arrays;
+//   * halo plan exchange between the ranks and the IPC-shared arena (vectors with ghost tails, reduction
+//     mailboxes, halo flags) that the kernels address directly over NVLink;
+//   * SpMV plan: tile plan for the TMA kernel, candidate configurations, on-device autotune.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+
+namespace bicg {
+
+void fatal(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fputc('\n', stderr);
+    exit(1);                       // the reference's error convention (solver.c:43-46, matrix.c:281-288)
+}
+
+// ------------------------------------------------------------------------------------------------
+// configuration
+// ------------------------------------------------------------------------------------------------
+int set_option(Config &c, const char *key, const char *value)
+{
+    std::string k(key);
+    if (k.rfind("BICG_", 0) == 0) k = k.substr(5);
+    auto as_int = [&] { return atoi(value); };
+    if (k == "TOL") c.tol = atof(value);
+    else if (k == "MAX_ITER") c.max_iter = as_int();
+    else if (k == "OUT_ITER") c.out_iter = as_int();
+    else if (k == "QUIET") c.quiet = as_int();
+    else if (k == "SPMV") {
+        std::string v(value);
+        c.spmv_kind = (v == "tma") ? 0 : (v == "rowsplit") ? 1 : -1;
+    }
+    else if (k == "SPMV_LANES") c.spmv_lanes = as_int();
+    else if (k == "SPMV_THREADS") c.spmv_threads = as_int();
+    else if (k == "SPMV_STAGES") c.spmv_stages = as_int();
+    else if (k == "SPMV_CTAS") c.spmv_ctas = as_int();
+    else if (k == "AUTOTUNE") c.autotune = as_int();
+    else if (k == "GRAPH") c.graph = as_int();
+    else if (k == "UNROLL") c.unroll = std::max(1, as_int());
+    else if (k == "CACHE") c.cache = as_int();
+    else if (k == "DEVICE") c.device = as_int();
+    else if (k == "HALO_GAP") c.halo_gap = std::max(0, as_int());
+    else if (k == "VERBOSE") c.verbose = as_int();
+    else return -1;
+    return 0;
+}
+
+void load_config_from_env(Config &c)
+{
+    static const char *keys[] = {"BICG_TOL", "BICG_MAX_ITER", "BICG_OUT_ITER", "BICG_QUIET", "BICG_SPMV",
+                                 "BICG_SPMV_LANES", "BICG_SPMV_THREADS", "BICG_SPMV_STAGES", "BICG_SPMV_CTAS",
+                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_DEVICE",
+                                 "BICG_HALO_GAP", "BICG_VERBOSE"};
+    for (const char *k : keys)
+        if (const char *v = getenv(k)) set_option(c, k, v);
+}
+
+Context &ctx()
+{
+    static Context *c = [] {
+        Context *p = new Context();
+        load_config_from_env(p->cfg);
+        return p;
+    }();
+    return *c;
+}
+
+void Context::ensure()
+{
+    if (ready) return;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        fatal("bicgstab_b200: no usable CUDA device (%s). This library has no CPU path.",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    int dev = cfg.device;
+    if (dev < 0) {
+        const char *lr = getenv("LOCAL_RANK");
+        dev = lr ? atoi(lr) : 0;
+    }
+    if (dev >= ndev) dev = dev % ndev;
+    BICG_CUDA(cudaSetDevice(dev));
+    device = dev;
+    cudaDeviceProp prop;
+    BICG_CUDA(cudaGetDeviceProperties(&prop, dev));
+    sm_count = prop.multiProcessorCount;
+    if (prop.major < 10)
+        fatal("bicgstab_b200: device %d (%s, sm_%d%d) is not a Blackwell GPU; this library ships sm_100a code only",
+              dev, prop.name, prop.major, prop.minor);
+    BICG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc = spmv_setup_attributes();
+    if (rc != 0) fatal("bicgstab_b200: cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)rc));
+    BICG_CUDA(cudaHostAlloc((void **)&h_flags, 64 * 4 * sizeof(int), cudaHostAllocDefault));
+    ready = true;
+}
+
+void Context::host_allgather(const void *send, void *recv, size_t bytes)
+{
+    if (world == 1) { memcpy(recv, send, bytes); return; }
+    if (!allgather) fatal("bicgstab_b200: world > 1 but no allgather callback (call bicg_comm_init)");
+    if (allgather(allgather_ctx, send, recv, bytes) != 0) fatal("bicgstab_b200: host allgather failed");
+}
+
+// ------------------------------------------------------------------------------------------------
+// SpMV planning
+// ------------------------------------------------------------------------------------------------
+static inline int round_up(long long v, int m) { return (int)(((v + m - 1) / m) * m); }
+
+static void free_plan(SpmvPlan &p)
+{
+    if (p.d_tile_row) cudaFree(p.d_tile_row);
+    if (p.d_tile_nz) cudaFree(p.d_tile_nz);
+    p.d_tile_row = nullptr; p.d_tile_nz = nullptr;
+}
+
+// Fill cap / smem / grid of a TMA-kernel candidate and build + upload its tile plan.  false: not feasible.
+static bool build_tma_plan(const bicg_matrix *m, const unsigned *h_ptr, int lanes, int threads, int stages,
+                           int want_ctas, SpmvPlan &out)
+{
+    Context &c = ctx();
+    const int rpt = threads / lanes;
+    const long long SMEM_MAX = 225 * 1024;
+    // stage capacity: a full tile of average rows with 25 % head-room, never less than the longest row
+    long long cap = (long long)std::ceil(rpt * m->mean_row * 1.25) + 64;
+    cap = std::max<long long>(cap, (long long)m->max_row + 16);
+    cap = round_up(cap, 32);
+    int ctas = want_ctas > 0 ? want_ctas : 2;
+    // shrink towards the shared-memory budget of `ctas` CTAs per SM
+    const long long budget = SMEM_MAX / ctas - 1024;
+    if ((long long)stages * cap * 12 > budget) {
+        long long fit = budget / (12LL * stages);
+        fit = (fit / 32) * 32;
+        if (fit < (long long)m->max_row + 16) return false;
+        cap = fit;
+    }
+    std::vector<int> tile_row;
+    int nt = plan_tiles(h_ptr, m->n_loc, rpt, (int)cap - 8, tile_row);
+    if (nt < 0) return false;
+    std::vector<unsigned> tile_nz(tile_row.size());
+    for (size_t i = 0; i < tile_row.size(); ++i) tile_nz[i] = h_ptr[tile_row[i]];
+
+    out.kind = 0; out.lanes = lanes; out.threads = threads; out.stages = stages; out.cap = (int)cap;
+    out.smem = spmv_tma_smem_bytes((int)cap, stages);
+    int by_smem = (int)std::max<long long>(1, SMEM_MAX / (long long)(out.smem + 1024));
+    out.ctas_per_sm = std::max(1, std::min({by_smem, 2048 / threads, want_ctas > 0 ? want_ctas : 8}));
+    out.ntiles = nt;
+    out.grid = std::max(1, std::min(nt, c.sm_count * out.ctas_per_sm));
+    BICG_CUDA(cudaMalloc((void **)&out.d_tile_row, tile_row.size() * sizeof(int)));
+    BICG_CUDA(cudaMalloc((void **)&out.d_tile_nz, tile_nz.size() * sizeof(unsigned)));
+    BICG_CUDA(cudaMemcpyAsync(out.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    BICG_CUDA(cudaMemcpyAsync(out.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+    BICG_CUDA(cudaStreamSynchronize(c.stream));   // the host vectors die here
+    return true;
+}
+
+static void build_rowsplit_plan(const bicg_matrix *m, int lanes, SpmvPlan &out)
+{
+    Context &c = ctx();
+    out = SpmvPlan();
+    out.kind = 1; out.lanes = lanes; out.threads = 256; out.stages = 0; out.cap = 0; out.smem = 0;
+    const int rpb = 256 / lanes;
+    long long blocks = ((long long)m->n_loc + rpb - 1) / rpb;
+    out.grid = (int)std::max<long long>(1, std::min<long long>(blocks, (long long)c.sm_count * 8));
+}
+
+static int heuristic_lanes(double mean_row)
+{
+    if (mean_row <= 24.0) return 1;
+    if (mean_row <= 48.0) return 8;
+    if (mean_row <= 128.0) return 16;
+    return 32;
+}
+
+SpmvArgs make_spmv_args(const bicg_matrix *m, const SpmvPlan &p, int x_id, int y_id)
+{
+    SpmvArgs a{};
+    a.kc.sc = m->d_sc; a.kc.partials = m->d_partials; a.kc.hist = m->d_hist; a.kc.comm = m->comm;
+    a.kc.tail = TailDesc{TAIL_NONE, FIN_NONE, 0, 0, 0, 0, 0};
+    a.val = m->d_val; a.col = m->d_col; a.ptr = m->d_ptr; a.rows = m->n_loc;
+    a.tile_row = p.d_tile_row; a.tile_nz = p.d_tile_nz; a.ntiles = p.ntiles; a.cap = p.cap; a.stages = p.stages;
+    a.x = m->vec(x_id); a.y = m->vec(y_id);
+    a.epi.ndot = 0;
+    a.wait_halo = (m->world > 1 && m->comm.recv_mask != 0) ? 1 : 0;
+    return a;
+}
+
+void launch_spmv_plan(const bicg_matrix *m, const SpmvPlan &p, const SpmvArgs &a, int prof_class)
+{
+    Context &c = ctx();
+    (void)m;
+    if (c.prof_on) {
+        cudaEvent_t e0, e1;
+        BICG_CUDA(cudaEventCreate(&e0)); BICG_CUDA(cudaEventCreate(&e1));
+        BICG_CUDA(cudaEventRecord(e0, c.stream));
+        int rc = launch_spmv(p.kind, p.lanes, p.threads, p.grid, p.smem, a, c.stream);
+        if (rc) fatal("bicgstab_b200: SpMV launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        BICG_CUDA(cudaEventRecord(e1, c.stream));
+        c.prof_ev.push_back(e0); c.prof_ev.push_back(e1); c.prof_class.push_back(prof_class);
+    } else {
+        int rc = launch_spmv(p.kind, p.lanes, p.threads, p.grid, p.smem, a, c.stream);
+        if (rc) fatal("bicgstab_b200: SpMV launch failed (kind %d lanes %d threads %d grid %d smem %zu): %s",
+                      p.kind, p.lanes, p.threads, p.grid, p.smem, cudaGetErrorString((cudaError_t)rc));
+    }
+    ++c.launches;
+}
+
+// time one candidate on the real matrix: x = V_P (whatever it holds), y = V_S, dot (r#, s) fused, no tail
+static double time_plan(bicg_matrix *m, const SpmvPlan &p, int reps)
+{
+    Context &c = ctx();
+    SpmvArgs a = make_spmv_args(m, p, V_P, V_S);
+    a.wait_halo = 0;
+    a.epi.ndot = 1; a.epi.a[0] = m->vec(V_RH); a.epi.b[0] = nullptr;
+    cudaEvent_t e0, e1;
+    BICG_CUDA(cudaEventCreate(&e0)); BICG_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) launch_spmv_plan(m, p, a);
+    BICG_CUDA(cudaEventRecord(e0, c.stream));
+    for (int i = 0; i < reps; ++i) launch_spmv_plan(m, p, a);
+    BICG_CUDA(cudaEventRecord(e1, c.stream));
+    BICG_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    BICG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return (double)ms / reps;
+}
+
+static void choose_spmv_plan(bicg_matrix *m, const unsigned *h_ptr)
+{
+    Context &c = ctx();
+    const Config &cfg = c.cfg;
+    const int LANES[6] = {1, 2, 4, 8, 16, 32};
+
+    auto fixed = [&](SpmvPlan &p) -> bool {
+        int lanes = cfg.spmv_lanes > 0 ? cfg.spmv_lanes : heuristic_lanes(m->mean_row);
+        if (cfg.spmv_kind == 1) { build_rowsplit_plan(m, lanes, p); return true; }
+        int threads = cfg.spmv_threads > 0 ? cfg.spmv_threads : 256;
+        int stages = cfg.spmv_stages > 0 ? cfg.spmv_stages : 3;
+        if (build_tma_plan(m, h_ptr, lanes, threads, stages, cfg.spmv_ctas, p)) return true;
+        if (build_tma_plan(m, h_ptr, lanes, threads, 2, 1, p)) return true;
+        if (cfg.spmv_kind == 0) return false;
+        build_rowsplit_plan(m, std::max(lanes, 8), p);
+        return true;
+    };
+
+    const bool pinned = cfg.spmv_lanes > 0 || cfg.spmv_threads > 0 || cfg.spmv_stages > 0 || cfg.spmv_ctas > 0;
+    if (!cfg.autotune || pinned || m->n_loc < 4096) {
+        if (!fixed(m->plan)) fatal("bicgstab_b200: requested SpMV configuration is not feasible for this matrix");
+        return;
+    }
+
+    // candidates: lanes around the mean row length x {128,256,512} threads x {2,3,4} stages x {1,2,3,4} CTAs/SM
+    std::vector<SpmvPlan> cands;
+    const int hl = heuristic_lanes(m->mean_row);
+    for (int li = 0; li < 6; ++li) {
+        const int lanes = LANES[li];
+        if (lanes > 2 * std::max(1.0, m->mean_row)) continue;
+        if (lanes < hl / 8) continue;
+        if (cfg.spmv_kind != 1) {
+            for (int threads : {128, 256, 512})
+                for (int stages : {2, 3, 4})
+                    for (int ctas : {1, 2, 4}) {
+                        if (threads * ctas > 2048) continue;
+                        SpmvPlan p;
+                        if (!build_tma_plan(m, h_ptr, lanes, threads, stages, ctas, p)) continue;
+                        if (p.ctas_per_sm != ctas) { free_plan(p); continue; }   // duplicate of another entry
+                        cands.push_back(p);
+                    }
+        }
+        if (cfg.spmv_kind != 0) {
+            SpmvPlan p; build_rowsplit_plan(m, lanes, p); cands.push_back(p);
+        }
+    }
+    if (cands.empty()) { if (!fixed(m->plan)) fatal("bicgstab_b200: no feasible SpMV configuration"); return; }
+
+    int best = -1;
+    for (size_t i = 0; i < cands.size(); ++i) {
+        cands[i].ms = time_plan(m, cands[i], 5);
+        if (cfg.verbose)
+            fprintf(stderr, "[bicg autotune r%d] kind=%d lanes=%2d threads=%3d stages=%d ctas=%d cap=%5d grid=%4d smem=%6zu : %.4f ms\n",
+                    m->rank, cands[i].kind, cands[i].lanes, cands[i].threads, cands[i].stages, cands[i].ctas_per_sm,
+                    cands[i].cap, cands[i].grid, cands[i].smem, cands[i].ms);
+        if (best < 0 || cands[i].ms < cands[best].ms) best = (int)i;
+    }
+    for (size_t i = 0; i < cands.size(); ++i)
+        if ((int)i != best) free_plan(cands[i]);
+    m->plan = cands[best];
+    if (cfg.verbose)
+        fprintf(stderr, "[bicg autotune r%d] chose kind=%d lanes=%d threads=%d stages=%d ctas=%d (%.4f ms)\n", m->rank,
+                m->plan.kind, m->plan.lanes, m->plan.threads, m->plan.stages, m->plan.ctas_per_sm, m->plan.ms);
+}
+
+// ------------------------------------------------------------------------------------------------
+// matrix creation
+// ------------------------------------------------------------------------------------------------
+struct ArenaHdr {
+    cudaIpcMemHandle_t handle;
+    long long vec_off, vstride, ghost_off, mail_off, hflag_off;
+    int n_loc, n_ghost;
+};
+
+bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info)
+{
+    Context &c = ctx();
+    c.ensure();
+    if (info->cols != info->rows) {                       // solver.c:43-46
+        printf("Error: matrix is not square.\n");
+        exit(1);
+    }
+    cudaEvent_t ev0, ev1;
+    BICG_CUDA(cudaEventCreate(&ev0)); BICG_CUDA(cudaEventCreate(&ev1));
+    BICG_CUDA(cudaEventRecord(ev0, c.stream));
+
+    bicg_matrix *m = new bicg_matrix();
+    m->rank = c.rank; m->world = c.world;
+    m->n_loc = (int)diag->rows; m->n_glob = (int)info->rows;
+    const size_t nd = diag->nz, no = (offd && m->world > 1) ? offd->nz : 0;
+    m->nnz = nd + no;
+    m->host_key = diag->val ? (const void *)diag->val : (const void *)diag;
+    m->ghost_off = round_up(m->n_loc, 16);
+
+    // ---- halo plan: which remote columns this rank needs, as merged runs -----------------------
+    std::vector<HaloRun> runs;
+    if (no) plan_halo_runs(offd, info, m->world, c.cfg.halo_gap, m->rank, runs);
+    int ghost = 0;
+    for (const HaloRun &r : runs) { m->recv_runs.insert(m->recv_runs.end(), {r.first, r.len, r.owner, ghost}); ghost += r.len; }
+    m->n_ghost = ghost;
+    m->vstride = (long long)m->ghost_off + round_up(std::max(ghost, 1), 16);
+
+    // ---- merged CSR over [own | ghost] columns -------------------------------------------------
+    const unsigned *h_ptr = diag->ptr;
+    std::vector<unsigned> mptr, mcol;
+    std::vector<double> mval;
+    const double *h_val = diag->val;
+    const unsigned *h_col = diag->col;
+    if (no) {
+        mptr.resize((size_t)m->n_loc + 1); mcol.resize(m->nnz); mval.resize(m->nnz);
+        std::vector<int> run_first(runs.size());
+        for (size_t i = 0; i < runs.size(); ++i) run_first[i] = runs[i].first;
+        size_t k = 0; mptr[0] = 0;
+        for (int i = 0; i < m->n_loc; ++i) {
+            for (unsigned j = diag->ptr[i]; j < diag->ptr[i + 1]; ++j) { mval[k] = diag->val[j]; mcol[k] = diag->col[j]; ++k; }   // matrix.c:437
+            for (unsigned j = offd->ptr[i]; j < offd->ptr[i + 1]; ++j) {                                                           // matrix.c:440
+                const int gc = (int)offd->col[j];
+                const size_t ri = (size_t)(std::upper_bound(run_first.begin(), run_first.end(), gc) - run_first.begin()) - 1;
+                mval[k] = offd->val[j];
+                mcol[k] = (unsigned)(m->ghost_off + m->recv_runs[4 * ri + 3] + (gc - runs[ri].first));
+                ++k;
+            }
+            mptr[(size_t)i + 1] = (unsigned)k;
+        }
+        h_ptr = mptr.data(); h_val = mval.data(); h_col = mcol.data();
+    }
+    unsigned max_row = 0;
+    for (int i = 0; i < m->n_loc; ++i) max_row = std::max(max_row, h_ptr[i + 1] - h_ptr[i]);
+    m->max_row = max_row;
+    m->mean_row = m->n_loc ? (double)m->nnz / m->n_loc : 0.0;
+
+    const size_t pad = 16;
+    BICG_CUDA(cudaMalloc((void **)&m->d_val, (m->nnz + pad) * sizeof(double)));
+    BICG_CUDA(cudaMalloc((void **)&m->d_col, (m->nnz + pad) * sizeof(unsigned)));
+    BICG_CUDA(cudaMalloc((void **)&m->d_ptr, ((size_t)m->n_loc + 1) * sizeof(unsigned)));
+    BICG_CUDA(cudaMemsetAsync(m->d_val + m->nnz, 0, pad * sizeof(double), c.stream));
+    BICG_CUDA(cudaMemsetAsync(m->d_col + m->nnz, 0, pad * sizeof(unsigned), c.stream));
+    if (m->nnz) {
+        BICG_CUDA(cudaMemcpyAsync(m->d_val, h_val, m->nnz * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        BICG_CUDA(cudaMemcpyAsync(m->d_col, h_col, m->nnz * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+    }
+    BICG_CUDA(cudaMemcpyAsync(m->d_ptr, h_ptr, ((size_t)m->n_loc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+    m->upload_bytes = m->nnz * 12 + ((size_t)m->n_loc + 1) * 4;
+
+    // ---- arena -------------------------------------------------------------------------------------
+    m->hist_cap = std::max(c.cfg.max_iter, 1000) + 2;
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    const size_t vec_off = off;   off = align(off + (size_t)V_COUNT * (size_t)m->vstride * sizeof(double));
+    const size_t sc_off = off;    off = align(off + sizeof(Scalars));
+    const size_t part_off = off;  off = align(off + (size_t)4096 * MAX_DOTS * sizeof(double));
+    const size_t hist_off = off;  off = align(off + (size_t)m->hist_cap * sizeof(double));
+    const size_t mail_off = off;  off = align(off + 2 * MAX_RANKS * sizeof(Mailbox));
+    const size_t hflag_off = off; off = align(off + MAX_RANKS * sizeof(HaloFlag));
+    m->arena_bytes = off;
+    BICG_CUDA(cudaMalloc((void **)&m->arena, m->arena_bytes));
+    BICG_CUDA(cudaMemsetAsync(m->arena, 0, m->arena_bytes, c.stream));
+    m->vec_base = (double *)(m->arena + vec_off);
+    m->d_sc = (Scalars *)(m->arena + sc_off);
+    m->d_partials = (double *)(m->arena + part_off);
+    m->d_hist = (double *)(m->arena + hist_off);
+    m->d_mail = (Mailbox *)(m->arena + mail_off);
+    m->d_hflag = (HaloFlag *)(m->arena + hflag_off);
+    BICG_CUDA(cudaStreamSynchronize(c.stream));            // arena zeroed before any peer may write into it
+
+    // ---- peers: exchange arena handles + layouts, then the halo runs -------------------------------
+    m->comm.rank = m->rank; m->comm.world = m->world;
+    for (int p = 0; p < MAX_RANKS; ++p) { m->comm.mail[p] = m->d_mail; m->comm.hflag[p] = m->d_hflag; }
+    if (m->world > 1) {
+        ArenaHdr mine{};
+        BICG_CUDA(cudaIpcGetMemHandle(&mine.handle, m->arena));
+        mine.vec_off = (long long)vec_off; mine.vstride = m->vstride; mine.ghost_off = m->ghost_off;
+        mine.mail_off = (long long)mail_off; mine.hflag_off = (long long)hflag_off;
+        mine.n_loc = m->n_loc; mine.n_ghost = m->n_ghost;
+        std::vector<ArenaHdr> all((size_t)m->world);
+        c.host_allgather(&mine, all.data(), sizeof(ArenaHdr));
+        for (int p = 0; p < m->world; ++p) {
+            if (p == m->rank) { m->peer_base[p] = m->arena; }
+            else BICG_CUDA(cudaIpcOpenMemHandle(&m->peer_base[p], all[(size_t)p].handle, cudaIpcMemLazyEnablePeerAccess));
+            m->peer_vec_off[p] = all[(size_t)p].vec_off; m->peer_vstride[p] = all[(size_t)p].vstride;
+            m->peer_ghost_off[p] = all[(size_t)p].ghost_off;
+            m->comm.mail[p] = (Mailbox *)((char *)m->peer_base[p] + all[(size_t)p].mail_off);
+            m->comm.hflag[p] = (HaloFlag *)((char *)m->peer_base[p] + all[(size_t)p].hflag_off);
+        }
+        // receive lists of every rank (variable length -> two rounds)
+        int my_cnt = (int)(m->recv_runs.size() / 4);
+        std::vector<int> cnts((size_t)m->world);
+        c.host_allgather(&my_cnt, cnts.data(), sizeof(int));
+        const int max_cnt = std::max(1, *std::max_element(cnts.begin(), cnts.end()));
+        std::vector<int> send((size_t)max_cnt * 4, 0), recv((size_t)max_cnt * 4 * (size_t)m->world);
+        std::copy(m->recv_runs.begin(), m->recv_runs.end(), send.begin());
+        c.host_allgather(send.data(), recv.data(), send.size() * sizeof(int));
+
+        unsigned recv_mask = 0, send_mask = 0;
+        for (int i = 0; i < my_cnt; ++i) recv_mask |= 1u << m->recv_runs[4 * (size_t)i + 2];
+        const int my_first = info->displs[m->rank];
+        for (int p = 0; p < m->world; ++p) {
+            if (p == m->rank) continue;
+            std::vector<PushRun> pr;
+            const int *rr = recv.data() + (size_t)p * (size_t)max_cnt * 4;
+            for (int i = 0; i < cnts[(size_t)p]; ++i)
+                if (rr[4 * i + 2] == m->rank) pr.push_back(PushRun{rr[4 * i] - my_first, rr[4 * i + 1], rr[4 * i + 3]});
+            if (pr.empty()) continue;
+            send_mask |= 1u << p;
+            const int slot = m->npush++;
+            m->push_peer[slot] = p; m->push_nruns[slot] = (int)pr.size();
+            BICG_CUDA(cudaMalloc((void **)&m->d_push_runs[slot], pr.size() * sizeof(PushRun)));
+            BICG_CUDA(cudaMemcpy(m->d_push_runs[slot], pr.data(), pr.size() * sizeof(PushRun), cudaMemcpyHostToDevice));
+        }
+        m->comm.recv_mask = recv_mask; m->comm.send_mask = send_mask;
+    }
+
+    // ---- fused-vector launch shape --------------------------------------------------------------------
+    m->vgrid = std::min(4096, std::max(1, std::min(c.sm_count * 4, (m->n_loc + 511) / 512)));
+    m->vchunk = round_up((m->n_loc + m->vgrid - 1) / m->vgrid, 2);
+    if (m->vchunk < 2) m->vchunk = 2;
+
+    // ---- SpMV plan ------------------------------------------------------------------------------------
+    choose_spmv_plan(m, h_ptr);
+
+    BICG_CUDA(cudaEventRecord(ev1, c.stream));
+    BICG_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    BICG_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    m->upload_ms = ms;
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (m->world > 1) {          // nobody may start pushing before every rank has mapped every arena
+        int token = 0; std::vector<int> all((size_t)m->world);
+        c.host_allgather(&token, all.data(), sizeof(int));
+    }
+    return m;
+}
+
+void matrix_destroy(bicg_matrix *m)
+{
+    if (!m) return;
+    Context &c = ctx();
+    if (c.ready) cudaStreamSynchronize(c.stream);
+    for (auto it = c.cache.begin(); it != c.cache.end();) {
+        if (it->second == m) it = c.cache.erase(it); else ++it;
+    }
+    for (int g = 0; g < 4; ++g) if (m->graph[g]) cudaGraphExecDestroy(m->graph[g]);
+    if (m->world > 1) {
+        int token = 0; std::vector<int> all((size_t)m->world);
+        c.host_allgather(&token, all.data(), sizeof(int));       // peers are done with my arena
+        for (int p = 0; p < m->world; ++p)
+            if (p != m->rank && m->peer_base[p]) cudaIpcCloseMemHandle(m->peer_base[p]);
+        c.host_allgather(&token, all.data(), sizeof(int));
+    }
+    for (int s = 0; s < m->npush; ++s) cudaFree(m->d_push_runs[s]);
+    free_plan(m->plan);
+    if (m->hist_extra) cudaFree(m->hist_extra);
+    cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_ptr); cudaFree(m->arena);
+    delete m;
+}
+
+bicg_matrix *matrix_get_cached(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, bool *fresh)
+{
+    Context &c = ctx();
+    const void *key = diag->val ? (const void *)diag->val : (const void *)diag;
+    if (c.cfg.cache) {
+        auto it = c.cache.find(key);
+        if (it != c.cache.end()) {
+            bicg_matrix *old = it->second;
+            if (old->n_loc == (int)diag->rows && old->n_glob == (int)info->rows && old->nnz == (size_t)diag->nz + (c.world > 1 && offd ? offd->nz : 0)) {
+                if (fresh) *fresh = false;
+                return old;
+            }
+            matrix_destroy(old);            // same arrays, different matrix: the caller reused the allocation
+        }
+    }
+    bicg_matrix *m = matrix_create(diag, offd, info);
+    if (fresh) *fresh = true;
+    if (c.cfg.cache) c.cache[key] = m;
+    return m;
+}
+
+} // namespace bicg
