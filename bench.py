@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- BiCGStab iterations/s on the BASELINE.json configs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload transport|laplace|random]
+                  [--method bicgstab|ca_bicgstab|pipe_bicgstab]
+
+One STEP = one complete solve of the workload (b = A*1, x0 = 0, to BICG_TOL / MAX_ITER of the config).
+  value : iterations/s, matrix + vectors resident in HBM when the timed region starts (CUDA events on the
+          library's stream around the K solves, max over ranks)
+  e2e   : the same metric through the reference-facing call bicgstab(A_diag, A_offd, A_info, x, r) on pinned
+          HOST buffers with the upload cache disabled: every step uploads the matrix and the vectors and reads
+          x and r back (wall clock around K calls, device idle on both sides)
+  roofline    : the fused SpMV + dot kernel (dominant kernel of every variant), algorithmic bytes
+                12*nnz + 28*n_loc per launch (SURVEY.md 8(d) phase P1) / average launch time from CUDA events
+  cpu_baseline: the reference's own sources (oracle/_ref, compiled in place) on this box's host cores, bounded
+                sample = the first REF_ITERS iterations of the same solve
+
+--impl reference times that CPU build alone (rank 0 only under torchrun).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs 2/4: Transport.mtx is not in the image (no network) -> T' surrogate of SURVEY.md 8(d)
+    "transport": dict(kind="stencil15", g=117, p0=14.0, tol=1e-8, max_iter=1000, method="bicgstab",
+                      label="T' = 15-pt stencil on 117^3 (n=1,601,613, nnz=23,616,325; Transport.mtx surrogate, "
+                            "diag=14 variant), b=A*1, x0=0, tol 1e-8"),
+    # config 3
+    "laplace": dict(kind="laplace5", g=2000, p0=0.0, tol=1e-8, max_iter=1000, method="pipe_bicgstab",
+                    label="5-pt Laplacian 2000^2 (n=4,000,000, nnz=19,992,000), b=A*1, x0=0, 1000 iterations max"),
+    # config 5 (per-GPU block 2 M rows x 32 nnz/row; n scales with the number of GPUs)
+    "random": dict(kind="random", g=2_000_000, p0=32, tol=1e-8, max_iter=1000, method="ca_bicgstab",
+                   label="random CSR, 2,000,000 rows per GPU x 32 nnz/row, b=A*1, x0=0, tol 1e-8"),
+}
+BYTES_PER_ITER_N = {"bicgstab": 160, "ca_bicgstab": 216, "pipe_bicgstab": 232}
+REF_ITERS = 20
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_array(B, shape, dtype):
+    import ctypes as C
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = B.lib.bicg_host_alloc(max(nbytes, 16))
+    buf = (C.c_char * max(nbytes, 16)).from_address(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def pinned_block(B, blk, rank, world):
+    """Copy a generated block into pinned host memory (the e2e leg's inputs live there)."""
+    import ctypes as C
+    out = B.MatrixBlock(world)
+    for src, dst, ncols in ((blk.diag, out.diag, blk.diag.cols), (blk.offd, out.offd, blk.offd.cols)):
+        val, col, ptr = B.MatrixBlock._view(src)
+        pv, pc, pp = pinned_array(B, max(val.size, 1), np.float64), pinned_array(B, max(col.size, 1), np.uint32), \
+            pinned_array(B, ptr.size, np.uint32)
+        pv[:val.size] = val; pc[:col.size] = col; pp[:] = ptr
+        dst.val = pv.ctypes.data_as(C.POINTER(C.c_double)); dst.col = pc.ctypes.data_as(C.POINTER(C.c_uint))
+        dst.ptr = pp.ctypes.data_as(C.POINTER(C.c_uint))
+        dst.nz, dst.rows, dst.cols = src.nz, src.rows, ncols
+        out._keep += [pv, pc, pp]
+    out.info.nz, out.info.rows, out.info.cols, out.info.code = blk.info.nz, blk.info.rows, blk.info.cols, b"MCRG"
+    for p in range(world):
+        out._recvcounts[p] = int(blk.recvcounts[p]); out._displs[p] = int(blk.displs[p])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+class RefRunner:
+    """The reference's own CPU code (oracle/_ref/ref_driver_fast + mini-MPI) on the same input.  The matrix is
+    written once to a binary file in /dev/shm; every run() is one `ref_driver` process tree."""
+
+    def __init__(self, w, cores=None):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        import mpi_bicgstab_b200 as B
+        self.O, self.w = O, w
+        self.ok = O.have_ref("ref_driver_fast")
+        if not self.ok:
+            return
+        self.cores = cores or min(len(os.sched_getaffinity(0)), 64)
+        blk = B.gen_block(w["kind"], w["g"], w["p0"])
+        ptr, col, val = B.block_to_global_csr(blk)
+        self.td = tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        self.file = os.path.join(self.td.name, "a.bin")
+        O.write_csr_bin(self.file, blk.n, ptr, col, val)
+        blk.free()
+
+    def run(self, n_iters):
+        res = self.O.ref_driver(self.w["method"], self.file, P=self.cores, rhs="a1", tol=0.0, max_iter=n_iters,
+                                flavour="fast", want_vectors=False, pin=True, timeout=1800)
+        res["cores"] = self.cores
+        return res
+
+    def close(self):
+        if self.ok:
+            self.td.cleanup()
+
+
+def reference_sample(w, n_iters):
+    rr = RefRunner(w)
+    if not rr.ok:
+        return None
+    try:
+        rr.run(max(2, n_iters // 4))          # page the file in, warm the cores
+        return rr.run(n_iters)
+    finally:
+        rr.close()
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rr = RefRunner(w)
+    if not rr.ok:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_fast is not built"}))
+        return
+    steps, times, its = args.steps, [], 0
+    try:
+        for s in range(args.warmup + steps):
+            r = rr.run(REF_ITERS)
+            if s >= args.warmup:
+                times.append(r["total_time_s"]); its += r["iters"]
+    finally:
+        rr.close()
+    total = sum(times)
+    val = its / total
+    line = {"metric": "BiCGStab iterations/sec", "value": val, "unit": "iterations/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": w["label"], "method": w["method"],
+                       "sample": f"first {REF_ITERS} iterations of the solve per step (reference's own timed region, solver.c:69-132)"},
+            "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": rr.cores, "kind": "reference",
+                             "sample": f"{REF_ITERS} iterations/step x {steps} steps, {rr.cores} ranks (fork+shm mini-MPI), gcc -O3 -march=x86-64-v3"},
+            "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+    import mpi_bicgstab_b200 as B
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    B.set_options(device=local, quiet=1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        B.comm_init_torch()
+    method = w["method"]
+    n_glob_g = w["g"] * world if w["kind"] == "random" else w["g"]
+
+    blk = B.gen_block(w["kind"], n_glob_g, w["p0"], rank=rank, world=world)
+    n_loc, n = blk.n_loc, blk.n
+    B.set_options(tol=w["tol"], max_iter=w["max_iter"])
+    dm = B.DeviceMatrix(blk)                                   # upload + plan (collective)
+    stream = torch.cuda.ExternalStream(B.lib.bicg_stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    import ctypes as C
+    st = B.bicg_stats()
+    with torch.cuda.stream(stream):
+        ones = np.ones(n_loc)
+        b_host = dm.spmv(ones)                                  # b = A*1 (main.c:109-113), collective
+        b_dev = torch.from_numpy(b_host).cuda()
+        x_dev = torch.zeros(n_loc, dtype=torch.float64, device="cuda")
+        r_dev = torch.empty_like(b_dev)
+
+        def resident_step():
+            x_dev.zero_(); r_dev.copy_(b_dev)
+            it = B.lib.bicg_solve(dm.h, B.METHODS[method], C.c_void_p(x_dev.data_ptr()), C.c_void_p(r_dev.data_ptr()),
+                                  0, 0, 1, C.byref(st))
+            return it, st.kernel_launches
+
+        for _ in range(args.warmup):
+            resident_step()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        iters, launches = 0, 0
+        for _ in range(args.steps):
+            it, nl = resident_step()
+            iters += it; launches += nl
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        final_res, converged = st.final_res, st.converged
+
+        # roofline of the dominant kernel, measured live (per rank; rank 0 reported)
+        peak, peak_src = measured_peak()
+        k_ms, k_bytes = dm.spmv_time(50)
+        prof_ms, prof_cnt = dm.profile(method, 50)
+        B.set_options(tol=w["tol"], max_iter=w["max_iter"])
+
+    # ---- e2e: reference-facing call on pinned host buffers, upload cache off --------------------------
+    B.set_options(cache=0)
+    pblk = pinned_block(B, blk, rank, world)
+    xh, rh = pinned_array(B, n_loc, np.float64), pinned_array(B, n_loc, np.float64)
+    h2d = d2h = 0
+    e2e_iters, t_e2e = 0, 0.0
+    for s in range(max(1, args.warmup // 2) + args.steps):
+        xh[:] = 0.0; rh[:] = b_host
+        barrier()
+        t0 = time.perf_counter()
+        it = B.solve(method, pblk, xh, rh)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if s >= max(1, args.warmup // 2):
+            e2e_iters += it; t_e2e += dt
+            s_ = B.last_stats(); h2d, d2h = s_["h2d_bytes"], s_["d2h_bytes"]
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    B.set_options(cache=1)
+
+    if rank == 0:
+        nnz_glob = int(blk.info.nz) if w["kind"] != "random" else n * int(w["p0"])
+        bytes_iter = 24 * nnz_glob + BYTES_PER_ITER_N[method] * n
+        line = {
+            "metric": "BiCGStab iterations/sec", "value": iters / (ms * 1e-3), "unit": "iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak" if w["kind"] == "random" else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["label"], "method": method, "iterations_per_step": iters / args.steps,
+                       "converged": bool(converged), "final_relative_residual": final_res,
+                       "l2": "inputs larger than L2 (matrix stream %.0f MB per SpMV > 126 MB L2)" % (12e-6 * blk.nnz_loc),
+                       "spmv_plan": {"kind": ["tma", "rowsplit"][st.spmv_kind], "lanes": st.spmv_lanes},
+                       "algorithmic_bytes_per_iteration": bytes_iter,
+                       "solver_effective_GBps": bytes_iter * iters / (ms * 1e-3) / 1e9},
+            "clocks": clocks,
+            "e2e": {"value": e2e_iters / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "spmv_tma_kernel + fused (r#,s) dot" if st.spmv_kind == 0 else "spmv_rowsplit_kernel + dot",
+                         "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": k_bytes / (k_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": k_bytes, "avg_launch_us": k_ms * 1e3,
+                         "traffic": read_traffic(),
+                         "in_solve": {"spmv_avg_us": 1e3 * prof_ms[0] / max(prof_cnt[0], 1),
+                                      "vector_avg_us": 1e3 * prof_ms[1] / max(prof_cnt[1], 1),
+                                      "spmv_share_of_step": prof_ms[0] / max(sum(prof_ms), 1e-12)}},
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                r = reference_sample(w, REF_ITERS)
+                if r:
+                    line["cpu_baseline"] = {"value": 1.0 / r["avg_time_per_iter_s"], "unit": "iterations/s",
+                                            "cores": r["cores"], "kind": "reference",
+                                            "sample": f"first {REF_ITERS} iterations of the same solve, reference sources compiled in place "
+                                                      f"(gcc -O3 -march=x86-64-v3), {r['cores']} ranks over a fork+shm mini-MPI"}
+            except Exception as exc:        # the GPU numbers must not be lost to a CPU-side hiccup
+                line["cpu_baseline"] = {"value": None, "unit": "iterations/s", "cores": 0, "kind": "reference",
+                                        "sample": f"failed: {exc!r}"}
+        print(json.dumps(line))
+    dm.destroy()
+    if world > 1:
+        B.comm_finalize()
+        dist.destroy_process_group()
+
+
+def read_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="transport", choices=sorted(WORKLOADS))
+    ap.add_argument("--method", default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.method:
+        w["method"] = args.method
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,18 @@ struct Config {
     int verbose = 0;
 };
 
+struct TuneKey {
+    int n_loc; size_t nnz; unsigned max_row; int kind;
+    bool operator<(const TuneKey &o) const
+    {
+        if (n_loc != o.n_loc) return n_loc < o.n_loc;
+        if (nnz != o.nnz) return nnz < o.nnz;
+        if (max_row != o.max_row) return max_row < o.max_row;
+        return kind < o.kind;
+    }
+};
+struct TuneVal { int kind, lanes, threads, stages, ctas; };
+
 struct Context {
     bool ready = false;
     Config cfg;
@@ -57,6 +69,7 @@ struct Context {
     bicg_stats last_stats{};
     // host-pointer keyed cache of uploaded matrices
     std::map<const void *, bicg_matrix *> cache;
+    std::map<TuneKey, TuneVal> tuned;     // SpMV autotune winners by matrix shape
     // pinned scratch
     int *h_flags = nullptr;      // ring of {k, max_iter, done, converged}
     // profiling of individual launches

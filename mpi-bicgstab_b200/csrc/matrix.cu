@@ -256,6 +256,14 @@ static void choose_spmv_plan(bicg_matrix *m, const unsigned *h_ptr)
         if (!fixed(m->plan)) fatal("bicgstab_b200: requested SpMV configuration is not feasible for this matrix");
         return;
     }
+    // a matrix of the same shape was tuned before in this process: reuse the winner
+    const TuneKey key{m->n_loc, m->nnz, m->max_row, cfg.spmv_kind};
+    auto hit = c.tuned.find(key);
+    if (hit != c.tuned.end()) {
+        const TuneVal &t = hit->second;
+        if (t.kind == 1) { build_rowsplit_plan(m, t.lanes, m->plan); return; }
+        if (build_tma_plan(m, h_ptr, t.lanes, t.threads, t.stages, t.ctas, m->plan)) return;
+    }
 
     // candidates: lanes around the mean row length x {128,256,512} threads x {2,3,4} stages x {1,2,3,4} CTAs/SM
     std::vector<SpmvPlan> cands;
@@ -293,6 +301,7 @@ static void choose_spmv_plan(bicg_matrix *m, const unsigned *h_ptr)
     for (size_t i = 0; i < cands.size(); ++i)
         if ((int)i != best) free_plan(cands[i]);
     m->plan = cands[best];
+    c.tuned[key] = TuneVal{m->plan.kind, m->plan.lanes, m->plan.threads, m->plan.stages, m->plan.ctas_per_sm};
     if (cfg.verbose)
         fprintf(stderr, "[bicg autotune r%d] chose kind=%d lanes=%d threads=%d stages=%d ctas=%d (%.4f ms)\n", m->rank,
                 m->plan.kind, m->plan.lanes, m->plan.threads, m->plan.stages, m->plan.ctas_per_sm, m->plan.ms);

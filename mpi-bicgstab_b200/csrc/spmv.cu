@@ -212,8 +212,12 @@ cudaError_t launch_rowsplit(int grid, const SpmvArgs &a, cudaStream_t st)
 template <int LANES, int THREADS>
 cudaError_t set_attr()
 {
+    // opt-in limit is 227 KB per CTA *including* the kernel's static shared memory
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, spmv_tma_kernel<LANES, THREADS>);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(spmv_tma_kernel<LANES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                227 * 1024);
+                                227 * 1024 - (int)fa.sharedSizeBytes);
 }
 template <int LANES>
 cudaError_t set_attr_l()

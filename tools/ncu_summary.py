@@ -1,0 +1,69 @@
+"""Summarise an .ncu-rep (key metrics per captured launch) and/or an ncu launch-list CSV into profiles/."""
+import csv
+import json
+import subprocess
+import sys
+from collections import defaultdict
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio"]
+
+
+def to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+def rep_summary(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    res = []
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        e = {"kernel": d.get("Kernel Name")}
+        for k in KEYS:
+            if k in d:
+                u = units[hdr.index(k)]
+                e[k] = to_bytes(d[k], u) if "bytes" in k else float(d[k].replace(",", ""))
+                if "bytes" not in k and u:
+                    e[k + ".unit"] = u
+        if "dram__bytes_read.sum" in e:
+            e["dram_bytes_total"] = e["dram__bytes_read.sum"] + e["dram__bytes_write.sum"]
+        res.append(e)
+    return res
+
+
+def launch_list(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    d = defaultdict(list)
+    for r in rows[1:]:
+        d[r[ki]].append(float(r[vi].replace(",", "")))
+    tot = sum(sum(v) for v in d.values())
+    return [{"kernel": k, "launches": len(v), "avg_us": sum(v) / len(v) / 1e3, "total_ms": sum(v) / 1e6,
+             "share": sum(v) / tot} for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1]))]
+
+
+if __name__ == "__main__":
+    out = {}
+    for p in sys.argv[1:]:
+        out[p] = rep_summary(p) if p.endswith(".ncu-rep") else launch_list(p)
+    print(json.dumps(out, indent=1))
