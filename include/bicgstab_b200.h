@@ -168,6 +168,22 @@ int  bicg_plan_tiles(const unsigned int *ptr, int rows, int rows_per_tile, int c
 int  bicg_plan_halo_runs(const CSR_Matrix *offd, const INFO_Matrix *info, int self, int world, int gap,
                          int *runs_out, int runs_cap);
 
+/* The device layout of rank `self`: its diag / offd blocks merged into one CSR over [own columns | ghost slots]
+ * (ghost slot g = column ghost_off + g; per row diag entries first, then offd, matrix.c:437-440).  Outputs are
+ * caller-allocated: ptr_out[rows+1], col_out/val_out[diag.nz + offd.nz], recv_out quadruples (first_col, len,
+ * owner, ghost_idx).  Returns the number of quadruples (or -needed ints if recv_cap is too small). */
+long long bicg_plan_merge(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, int self, int world,
+                          int gap, int ghost_off, unsigned int *ptr_out, unsigned int *col_out, double *val_out,
+                          int *recv_out, int recv_cap, int *n_ghost_out);
+/* round trip of a few bytes through the registered allgather callback; 0 = every rank's contribution arrived */
+int  bicg_comm_selftest(void);
+
+/* What rank `self` pushes to rank `dest`, derived from every rank's receive list (quadruples first_col, len,
+ * owner, ghost_idx; `stride` ints reserved per rank, cnts[p] quadruples valid).  Writes triples
+ * (local_src_row, len, ghost_offset_on_dest); returns their number (or -needed). */
+int  bicg_plan_push_runs(const int *all_recv, const int *cnts, int stride, int self, int dest, int my_first,
+                         int *out, int out_cap);
+
 /* Synthetic inputs of SURVEY.md 8(d) / BASELINE.json configs, generated directly as one rank's blocks
  * (malloc'ed like the reference loader's, so csr_free_matrix() releases them).  info->recvcounts/displs
  * must be caller-allocated with `world` entries (main.c:82-83).

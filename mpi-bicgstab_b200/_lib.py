@@ -68,6 +68,10 @@ SYMBOLS = {
     "bicg_plan_partition": (None, [C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
     "bicg_plan_tiles": (C.c_int, [_P(C.c_uint), C.c_int, C.c_int, C.c_int, _P(C.c_int), C.c_int]),
     "bicg_plan_halo_runs": (C.c_int, [_P(CSR_Matrix), _P(INFO_Matrix), C.c_int, C.c_int, C.c_int, _P(C.c_int), C.c_int]),
+    "bicg_plan_merge": (C.c_longlong, [_P(CSR_Matrix), _P(CSR_Matrix), _P(INFO_Matrix), C.c_int, C.c_int, C.c_int, C.c_int,
+                                       _P(C.c_uint), _P(C.c_uint), _P(C.c_double), _P(C.c_int), C.c_int, _P(C.c_int)]),
+    "bicg_comm_selftest": (C.c_int, []),
+    "bicg_plan_push_runs": (C.c_int, [_P(C.c_int), _P(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_int), C.c_int]),
     "bicg_gen_block": (C.c_int, [C.c_int, C.c_longlong, C.c_double, C.c_uint64, C.c_int, C.c_int,
                                  _P(CSR_Matrix), _P(CSR_Matrix), _P(INFO_Matrix)]),
     "bicg_shm_bootstrap": (C.c_int, []),

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <ctime>
 
 using namespace bicg;
 
@@ -26,14 +27,21 @@ int run_reference_entry(int method, CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *i
     Context &c = ctx();
     c.ensure();
     bool fresh = false;
+    auto wall = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec; };
+    const double t0 = wall();
     bicg_matrix *m = matrix_get_cached(D, O, info, &fresh);
+    const double t1 = wall();
     bicg_stats st{};
     solve(m, method, x, r, krr, nrr, 0, &st);
+    const double t2 = wall();
     st.upload_ms = fresh ? m->upload_ms : 0.0;
     st.h2d_bytes += fresh ? m->upload_bytes : 0;
     c.last_stats = st;
     print_reference_lines(st, c.last_hist);
     if (!c.cfg.cache) matrix_destroy(m);
+    if (c.cfg.verbose >= 2)
+        fprintf(stderr, "[bicg entry r%d] matrix %.3f ms (fresh %d), solve call %.3f ms (loop %.3f ms), destroy %.3f ms\n", c.rank,
+                t1 - t0, (int)fresh, t2 - t1, st.loop_ms, wall() - t2);
     return st.iters;
 }
 
@@ -89,6 +97,16 @@ void bicg_comm_finalize(void)
     for (bicg_matrix *m : ms) matrix_destroy(m);
     c.cache.clear();
     c.rank = 0; c.world = 1; c.allgather = nullptr; c.allgather_ctx = nullptr;
+}
+int bicg_comm_selftest(void)
+{
+    Context &c = ctx();
+    struct Probe { int rank, world; unsigned magic; } mine{c.rank, c.world, 0xB1C65AB0u + (unsigned)c.rank};
+    std::vector<Probe> all((size_t)c.world);
+    c.host_allgather(&mine, all.data(), sizeof(Probe));
+    for (int p = 0; p < c.world; ++p)
+        if (all[(size_t)p].rank != p || all[(size_t)p].world != c.world || all[(size_t)p].magic != 0xB1C65AB0u + (unsigned)p) return 1;
+    return 0;
 }
 int bicg_comm_rank(void) { return ctx().rank; }
 int bicg_comm_world(void) { return ctx().world; }

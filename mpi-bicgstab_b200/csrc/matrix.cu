@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <ctime>
 
 namespace bicg {
 
@@ -128,16 +129,17 @@ static bool build_tma_plan(const bicg_matrix *m, const unsigned *h_ptr, int lane
 {
     Context &c = ctx();
     const int rpt = threads / lanes;
-    const long long SMEM_MAX = 225 * 1024;
+    const long long SMEM_MAX = 224 * 1024;
+    const long long fixed = (long long)(rpt + 8) * 36;        // ptr slice + 4 epilogue slices per stage (spmv.cu)
     // stage capacity: a full tile of average rows with 25 % head-room, never less than the longest row
     long long cap = (long long)std::ceil(rpt * m->mean_row * 1.25) + 64;
     cap = std::max<long long>(cap, (long long)m->max_row + 16);
     cap = round_up(cap, 32);
     int ctas = want_ctas > 0 ? want_ctas : 2;
     // shrink towards the shared-memory budget of `ctas` CTAs per SM
-    const long long budget = SMEM_MAX / ctas - 1024;
-    if ((long long)stages * cap * 12 > budget) {
-        long long fit = budget / (12LL * stages);
+    const long long budget = SMEM_MAX / ctas - 1536;
+    if ((long long)stages * (cap * 12 + fixed) > budget) {
+        long long fit = (budget / stages - fixed) / 12;
         fit = (fit / 32) * 32;
         if (fit < (long long)m->max_row + 16) return false;
         cap = fit;
@@ -149,9 +151,9 @@ static bool build_tma_plan(const bicg_matrix *m, const unsigned *h_ptr, int lane
     for (size_t i = 0; i < tile_row.size(); ++i) tile_nz[i] = h_ptr[tile_row[i]];
 
     out.kind = 0; out.lanes = lanes; out.threads = threads; out.stages = stages; out.cap = (int)cap;
-    out.smem = spmv_tma_smem_bytes((int)cap, stages);
-    int by_smem = (int)std::max<long long>(1, SMEM_MAX / (long long)(out.smem + 1024));
-    out.ctas_per_sm = std::max(1, std::min({by_smem, 2048 / threads, want_ctas > 0 ? want_ctas : 8}));
+    out.smem = spmv_tma_smem_bytes((int)cap, stages, threads, lanes);
+    int by_smem = (int)std::max<long long>(1, SMEM_MAX / (long long)(out.smem + 1536));
+    out.ctas_per_sm = std::max(1, std::min({by_smem, 2048 / (threads + 32), want_ctas > 0 ? want_ctas : 8}));
     out.ntiles = nt;
     out.grid = std::max(1, std::min(nt, c.sm_count * out.ctas_per_sm));
     BICG_CUDA(cudaMalloc((void **)&out.d_tile_row, tile_row.size() * sizeof(int)));
@@ -188,7 +190,7 @@ SpmvArgs make_spmv_args(const bicg_matrix *m, const SpmvPlan &p, int x_id, int y
     a.val = m->d_val; a.col = m->d_col; a.ptr = m->d_ptr; a.rows = m->n_loc;
     a.tile_row = p.d_tile_row; a.tile_nz = p.d_tile_nz; a.ntiles = p.ntiles; a.cap = p.cap; a.stages = p.stages;
     a.x = m->vec(x_id); a.y = m->vec(y_id);
-    a.epi.ndot = 0;
+    a.epi = EpiArgs{};
     a.wait_halo = (m->world > 1 && m->comm.recv_mask != 0) ? 1 : 0;
     return a;
 }
@@ -219,7 +221,7 @@ static double time_plan(bicg_matrix *m, const SpmvPlan &p, int reps)
     Context &c = ctx();
     SpmvArgs a = make_spmv_args(m, p, V_P, V_S);
     a.wait_halo = 0;
-    a.epi.ndot = 1; a.epi.a[0] = m->vec(V_RH); a.epi.b[0] = nullptr;
+    epi_add_dot(a.epi, m->vec(V_RH), nullptr);
     cudaEvent_t e0, e1;
     BICG_CUDA(cudaEventCreate(&e0)); BICG_CUDA(cudaEventCreate(&e1));
     for (int i = 0; i < 2; ++i) launch_spmv_plan(m, p, a);
@@ -276,7 +278,7 @@ static void choose_spmv_plan(bicg_matrix *m, const unsigned *h_ptr)
             for (int threads : {128, 256, 512})
                 for (int stages : {2, 3, 4})
                     for (int ctas : {1, 2, 4}) {
-                        if (threads * ctas > 2048) continue;
+                        if ((threads + 32) * ctas > 2048) continue;
                         SpmvPlan p;
                         if (!build_tma_plan(m, h_ptr, lanes, threads, stages, ctas, p)) continue;
                         if (p.ctas_per_sm != ctas) { free_plan(p); continue; }   // duplicate of another entry
@@ -316,10 +318,25 @@ struct ArenaHdr {
     int n_loc, n_ghost;
 };
 
+static double now_ms()
+{
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
 bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info)
 {
     Context &c = ctx();
     c.ensure();
+    const double t_begin = now_ms();
+    double t_mark = t_begin;
+    auto lap = [&](const char *what) {
+        if (c.cfg.verbose < 2) return;
+        cudaStreamSynchronize(c.stream);
+        const double t = now_ms();
+        fprintf(stderr, "[bicg create r%d] %-28s %8.3f ms\n", c.rank, what, t - t_mark);
+        t_mark = t;
+    };
     if (info->cols != info->rows) {                       // solver.c:43-46
         printf("Error: matrix is not square.\n");
         exit(1);
@@ -336,38 +353,17 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     m->host_key = diag->val ? (const void *)diag->val : (const void *)diag;
     m->ghost_off = round_up(m->n_loc, 16);
 
-    // ---- halo plan: which remote columns this rank needs, as merged runs -----------------------
-    std::vector<HaloRun> runs;
-    if (no) plan_halo_runs(offd, info, m->world, c.cfg.halo_gap, m->rank, runs);
-    int ghost = 0;
-    for (const HaloRun &r : runs) { m->recv_runs.insert(m->recv_runs.end(), {r.first, r.len, r.owner, ghost}); ghost += r.len; }
-    m->n_ghost = ghost;
-    m->vstride = (long long)m->ghost_off + round_up(std::max(ghost, 1), 16);
-
-    // ---- merged CSR over [own | ghost] columns -------------------------------------------------
+    // ---- halo plan + merged CSR over [own | ghost] columns (plan.cpp) ------------------------------
     const unsigned *h_ptr = diag->ptr;
-    std::vector<unsigned> mptr, mcol;
-    std::vector<double> mval;
     const double *h_val = diag->val;
     const unsigned *h_col = diag->col;
+    std::vector<unsigned> mptr, mcol;
+    std::vector<double> mval;
     if (no) {
-        mptr.resize((size_t)m->n_loc + 1); mcol.resize(m->nnz); mval.resize(m->nnz);
-        std::vector<int> run_first(runs.size());
-        for (size_t i = 0; i < runs.size(); ++i) run_first[i] = runs[i].first;
-        size_t k = 0; mptr[0] = 0;
-        for (int i = 0; i < m->n_loc; ++i) {
-            for (unsigned j = diag->ptr[i]; j < diag->ptr[i + 1]; ++j) { mval[k] = diag->val[j]; mcol[k] = diag->col[j]; ++k; }   // matrix.c:437
-            for (unsigned j = offd->ptr[i]; j < offd->ptr[i + 1]; ++j) {                                                           // matrix.c:440
-                const int gc = (int)offd->col[j];
-                const size_t ri = (size_t)(std::upper_bound(run_first.begin(), run_first.end(), gc) - run_first.begin()) - 1;
-                mval[k] = offd->val[j];
-                mcol[k] = (unsigned)(m->ghost_off + m->recv_runs[4 * ri + 3] + (gc - runs[ri].first));
-                ++k;
-            }
-            mptr[(size_t)i + 1] = (unsigned)k;
-        }
+        merge_blocks(diag, offd, info, m->rank, m->world, c.cfg.halo_gap, m->ghost_off, mptr, mcol, mval, m->recv_runs, m->n_ghost);
         h_ptr = mptr.data(); h_val = mval.data(); h_col = mcol.data();
     }
+    m->vstride = (long long)m->ghost_off + round_up(std::max(m->n_ghost, 1), 16);
     unsigned max_row = 0;
     for (int i = 0; i < m->n_loc; ++i) max_row = std::max(max_row, h_ptr[i + 1] - h_ptr[i]);
     m->max_row = max_row;
@@ -376,7 +372,8 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     const size_t pad = 16;
     BICG_CUDA(cudaMalloc((void **)&m->d_val, (m->nnz + pad) * sizeof(double)));
     BICG_CUDA(cudaMalloc((void **)&m->d_col, (m->nnz + pad) * sizeof(unsigned)));
-    BICG_CUDA(cudaMalloc((void **)&m->d_ptr, ((size_t)m->n_loc + 1) * sizeof(unsigned)));
+    BICG_CUDA(cudaMalloc((void **)&m->d_ptr, ((size_t)m->n_loc + 1 + pad) * sizeof(unsigned)));
+    BICG_CUDA(cudaMemsetAsync(m->d_ptr + m->n_loc + 1, 0, pad * sizeof(unsigned), c.stream));
     BICG_CUDA(cudaMemsetAsync(m->d_val + m->nnz, 0, pad * sizeof(double), c.stream));
     BICG_CUDA(cudaMemsetAsync(m->d_col + m->nnz, 0, pad * sizeof(unsigned), c.stream));
     if (m->nnz) {
@@ -386,6 +383,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     BICG_CUDA(cudaMemcpyAsync(m->d_ptr, h_ptr, ((size_t)m->n_loc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
     m->upload_bytes = m->nnz * 12 + ((size_t)m->n_loc + 1) * 4;
 
+    lap("merge + alloc + H2D matrix");
     // ---- arena -------------------------------------------------------------------------------------
     m->hist_cap = std::max(c.cfg.max_iter, 1000) + 2;
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -407,6 +405,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     m->d_hflag = (HaloFlag *)(m->arena + hflag_off);
     BICG_CUDA(cudaStreamSynchronize(c.stream));            // arena zeroed before any peer may write into it
 
+    lap("arena alloc + zero");
     // ---- peers: exchange arena handles + layouts, then the halo runs -------------------------------
     m->comm.rank = m->rank; m->comm.world = m->world;
     for (int p = 0; p < MAX_RANKS; ++p) { m->comm.mail[p] = m->d_mail; m->comm.hflag[p] = m->d_hflag; }
@@ -440,11 +439,11 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
         const int my_first = info->displs[m->rank];
         for (int p = 0; p < m->world; ++p) {
             if (p == m->rank) continue;
-            std::vector<PushRun> pr;
-            const int *rr = recv.data() + (size_t)p * (size_t)max_cnt * 4;
-            for (int i = 0; i < cnts[(size_t)p]; ++i)
-                if (rr[4 * i + 2] == m->rank) pr.push_back(PushRun{rr[4 * i] - my_first, rr[4 * i + 1], rr[4 * i + 3]});
-            if (pr.empty()) continue;
+            std::vector<PushRunHost> ph;
+            plan_push_runs(recv.data(), cnts.data(), max_cnt * 4, m->rank, p, my_first, ph);
+            if (ph.empty()) continue;
+            std::vector<PushRun> pr(ph.size());
+            for (size_t i = 0; i < ph.size(); ++i) pr[i] = PushRun{ph[i].src, ph[i].len, ph[i].dst_off};
             send_mask |= 1u << p;
             const int slot = m->npush++;
             m->push_peer[slot] = p; m->push_nruns[slot] = (int)pr.size();
@@ -454,14 +453,16 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
         m->comm.recv_mask = recv_mask; m->comm.send_mask = send_mask;
     }
 
+    lap("peer exchange");
     // ---- fused-vector launch shape --------------------------------------------------------------------
-    m->vgrid = std::min(4096, std::max(1, std::min(c.sm_count * 4, (m->n_loc + 511) / 512)));
-    m->vchunk = round_up((m->n_loc + m->vgrid - 1) / m->vgrid, 2);
-    if (m->vchunk < 2) m->vchunk = 2;
+    m->vgrid = std::min(4096, std::max(1, std::min(c.sm_count * 6, (m->n_loc + 1023) / 1024)));
+    m->vchunk = round_up((m->n_loc + m->vgrid - 1) / m->vgrid, 4);
+    if (m->vchunk < 4) m->vchunk = 4;
 
     // ---- SpMV plan ------------------------------------------------------------------------------------
     choose_spmv_plan(m, h_ptr);
 
+    lap("spmv plan");
     BICG_CUDA(cudaEventRecord(ev1, c.stream));
     BICG_CUDA(cudaEventSynchronize(ev1));
     float ms = 0.f;

@@ -65,7 +65,82 @@ void plan_halo_runs(const CSR_Matrix *offd, const INFO_Matrix *info, int world, 
     }
 }
 
+// Merge the reference's two blocks of one rank into a single CSR over the extended local column space:
+// columns [0, n_loc) are the rank's own, columns ghost_off + g are ghost slot g.  Per row the diag entries come
+// first, then the offd entries -- the order in which the reference accumulates them (matrix.c:437, 440).
+// recv gets quadruples (first_col, len, owner, ghost_idx) describing which global columns fill the ghost slots.
+void merge_blocks(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, int self, int world, int gap,
+                  int ghost_off, std::vector<unsigned> &mptr, std::vector<unsigned> &mcol, std::vector<double> &mval,
+                  std::vector<int> &recv, int &n_ghost)
+{
+    std::vector<HaloRun> runs;
+    const bool far = offd && offd->nz > 0 && world > 1;
+    if (far) plan_halo_runs(offd, info, world, gap, self, runs);
+    recv.clear();
+    int ghost = 0;
+    for (const HaloRun &r : runs) { recv.insert(recv.end(), {r.first, r.len, r.owner, ghost}); ghost += r.len; }
+    n_ghost = ghost;
+    const int n_loc = (int)diag->rows;
+    const size_t nnz = (size_t)diag->nz + (far ? (size_t)offd->nz : 0);
+    mptr.resize((size_t)n_loc + 1); mcol.resize(nnz); mval.resize(nnz);
+    std::vector<int> run_first(runs.size());
+    for (size_t i = 0; i < runs.size(); ++i) run_first[i] = runs[i].first;
+    size_t k = 0;
+    mptr[0] = 0;
+    for (int i = 0; i < n_loc; ++i) {
+        for (unsigned j = diag->ptr[i]; j < diag->ptr[i + 1]; ++j) { mval[k] = diag->val[j]; mcol[k] = diag->col[j]; ++k; }
+        if (far)
+            for (unsigned j = offd->ptr[i]; j < offd->ptr[i + 1]; ++j) {
+                const int gc = (int)offd->col[j];
+                const size_t ri = (size_t)(std::upper_bound(run_first.begin(), run_first.end(), gc) - run_first.begin()) - 1;
+                mval[k] = offd->val[j];
+                mcol[k] = (unsigned)(ghost_off + recv[4 * ri + 3] + (gc - runs[ri].first));
+                ++k;
+            }
+        mptr[(size_t)i + 1] = (unsigned)k;
+    }
+}
+
+// From every rank's receive list (quadruples first_col, len, owner, ghost_idx; `stride` ints per rank, cnts[p]
+// valid quadruples) derive what rank `self` must push to rank `dest`: local source run -> ghost offset on dest.
+void plan_push_runs(const int *all_recv, const int *cnts, int stride, int self, int dest, int my_first,
+                    std::vector<PushRunHost> &out)
+{
+    out.clear();
+    const int *rr = all_recv + (size_t)dest * (size_t)stride;
+    for (int i = 0; i < cnts[dest]; ++i)
+        if (rr[4 * i + 2] == self) out.push_back(PushRunHost{rr[4 * i] - my_first, rr[4 * i + 1], rr[4 * i + 3]});
+}
+
 } // namespace bicg
+
+extern "C" int bicg_plan_push_runs(const int *all_recv, const int *cnts, int stride, int self, int dest, int my_first,
+                                   int *out, int out_cap)
+{
+    std::vector<bicg::PushRunHost> v;
+    bicg::plan_push_runs(all_recv, cnts, stride, self, dest, my_first, v);
+    if ((int)v.size() > out_cap) return -(int)v.size();
+    for (size_t i = 0; i < v.size(); ++i) { out[3 * i] = v[i].src; out[3 * i + 1] = v[i].len; out[3 * i + 2] = v[i].dst_off; }
+    return (int)v.size();
+}
+
+extern "C" long long bicg_plan_merge(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, int self,
+                                     int world, int gap, int ghost_off, unsigned *ptr_out, unsigned *col_out,
+                                     double *val_out, int *recv_out, int recv_cap, int *n_ghost_out)
+{
+    std::vector<unsigned> mptr, mcol;
+    std::vector<double> mval;
+    std::vector<int> recv;
+    int n_ghost = 0;
+    bicg::merge_blocks(diag, offd, info, self, world, gap, ghost_off, mptr, mcol, mval, recv, n_ghost);
+    if ((int)recv.size() > recv_cap) return -(long long)recv.size();
+    std::memcpy(ptr_out, mptr.data(), mptr.size() * sizeof(unsigned));
+    std::memcpy(col_out, mcol.data(), mcol.size() * sizeof(unsigned));
+    std::memcpy(val_out, mval.data(), mval.size() * sizeof(double));
+    std::memcpy(recv_out, recv.data(), recv.size() * sizeof(int));
+    *n_ghost_out = n_ghost;
+    return (long long)(recv.size() / 4);
+}
 
 extern "C" int bicg_plan_tiles(const unsigned int *ptr, int rows, int rows_per_tile, int cap_nnz,
                                int *tile_row, int tile_row_cap)

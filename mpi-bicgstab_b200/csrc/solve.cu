@@ -99,9 +99,8 @@ struct Seq {
     {
         SpmvArgs a = make_spmv_args(m, m->plan, x_id, y_id);
         a.kc.tail = tail;
-        a.epi.ndot = ndot;
-        a.epi.a[0] = a0; a.epi.b[0] = b0; a.epi.a[1] = a1; a.epi.b[1] = b1;
-        a.epi.a[2] = a2; a.epi.b[2] = b2; a.epi.a[3] = a3; a.epi.b[3] = b3;
+        const double *as[4] = {a0, a1, a2, a3}, *bs[4] = {b0, b1, b2, b3};
+        for (int k = 0; k < ndot; ++k) epi_add_dot(a.epi, as[k], bs[k]);
         launch_spmv_plan(m, m->plan, a, 0);
         ++launches;
     }
@@ -377,7 +376,7 @@ int spmv_time(bicg_matrix *m, int reps, double *ms_out, double *bytes_out)
     fill_kernel<<<256, 256, 0, c.stream>>>(m->vec(V_RH), m->n_loc, 1.0);
     SpmvArgs a = make_spmv_args(m, m->plan, V_P, V_S);
     a.wait_halo = 0;
-    a.epi.ndot = 1; a.epi.a[0] = m->vec(V_RH); a.epi.b[0] = nullptr;
+    epi_add_dot(a.epi, m->vec(V_RH), nullptr);
     a.kc.tail = tail_pend(1, 0);               // full in-kernel reduction of the dot, no peer traffic
     cudaEvent_t e0, e1;
     BICG_CUDA(cudaEventCreate(&e0)); BICG_CUDA(cudaEventCreate(&e1));

@@ -3,17 +3,20 @@
 // (matrix.c:498-516, 428-441) and the my_ddot + MPI_Iallreduce pairs that follow them (solver.c:88-91,
 // 96-102, 238-247, 365-367, 381-385).
 //
-// Two kernels:
-//
-//  spmv_tma_kernel<LANES, THREADS>   (kind 0, the default)
-//      Persistent CTAs walk a precomputed tile plan (<= THREADS/LANES rows and <= cap entries per tile).
-//      One elected thread streams each tile's val[] / col[] slices from HBM into a multi-stage shared-memory
-//      ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx; UBLKCP in SASS), so the DRAM
-//      stream is fully coalesced, asynchronous and independent of the row structure.  LANES threads then
-//      consume one row from shared memory.  With LANES = 1 a warp's 32 gathers x[col] at step j hit the
-//      same stencil offset of 32 consecutive rows -> 2 cache lines instead of ~15 for banded matrices, and
-//      the row is summed left to right exactly like the reference's scalar loop.  LANES > 1 is for long /
-//      irregular rows (shuffle reduction inside the LANES group).
+//  spmv_ws_kernel<LANES, CTHREADS>   (kind 0, the default) -- warp-specialised, TMA-fed
+//      Persistent CTAs walk a precomputed tile plan (<= CTHREADS/LANES rows and <= cap entries per tile).
+//      One PRODUCER warp streams, per tile, everything the consumers will touch except x itself -- the val[]
+//      and col[] slices, the ptr[] slice of the tile's rows and the slices of the epilogue vectors (r#, q, ...)
+//      -- from HBM into a multi-stage shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//      complete_tx; UBLKCP in SASS).  CTHREADS/32 CONSUMER warps wait on the stage's "full" mbarrier, consume
+//      it and arrive on its "empty" mbarrier; there is no CTA-wide barrier in the loop, so a slow warp never
+//      stalls the others and the only long-latency operation left on a consumer's critical path is the
+//      gather x[col] (issued 16 at a time per thread so a row costs one L2 round trip).
+//      With LANES = 1 a warp's 32 gathers at step j hit the same stencil offset of 32 consecutive rows -> 2
+//      cache lines instead of ~15 for banded matrices, and the row is summed left to right exactly like the
+//      reference's scalar loop.  LANES > 1 is for long / irregular rows (shuffle reduction in the group).
+//      (Round-1 history: the first version used one __syncthreads per tile and loaded ptr / r# from global
+//      inside the loop; ncu showed 76 % of cycles with no eligible warp -- profiles/r01a_first_path.json.)
 //
 //  spmv_rowsplit_kernel<LANES>       (kind 1)
 //      Classic sub-warp-per-row kernel reading val/col straight from global memory; fallback for matrices
@@ -34,108 +37,152 @@ __device__ __forceinline__ double lanes_sum(double v)
     return v;
 }
 
-__device__ __forceinline__ void row_epilogue(const SpmvArgs &a, int row, double yi, double (&dot)[4])
-{
-    a.y[row] = yi;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k < a.epi.ndot) {
-            const double av = a.epi.a[k] ? a.epi.a[k][row] : yi;
-            const double bv = a.epi.b[k] ? a.epi.b[k][row] : yi;
-            dot[k] = fma(av, bv, dot[k]);
-        }
-    }
-}
-
 __device__ __forceinline__ bool needs_tail(const KernelCommon &kc)
 {
     return kc.tail.op != TAIL_NONE || kc.tail.signal_halo;
 }
 
-template <int LANES, int THREADS>
-__global__ void __launch_bounds__(THREADS) spmv_tma_kernel(const __grid_constant__ SpmvArgs a)
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+constexpr int PROW_PAD = 8;       // extra ptr / epilogue slots per stage for the 16-byte alignment window
+
+struct StageHdr { int row0, row1; unsigned a0; int rowa; };
+
+template <int LANES, int CTHREADS>
+__global__ void __launch_bounds__(CTHREADS + 32, 1) spmv_ws_kernel(const __grid_constant__ SpmvArgs a)
 {
     if (a.kc.sc->done) return;
 
+    constexpr int RPT = CTHREADS / LANES;            // rows per tile
+    constexpr int PROW = RPT + PROW_PAD;
+    constexpr int NCW = CTHREADS / 32;               // consumer warps
+    constexpr int UNR = (LANES == 1) ? 16 : 8;       // gathers in flight per thread
+
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ __align__(8) unsigned long long bars[4];
+    __shared__ __align__(8) unsigned long long full_bar[4], empty_bar[4];
+    __shared__ StageHdr hdr[4];
     __shared__ double scratch[32 * 4];
 
     const int tid = threadIdx.x;
-    const int lane = tid % LANES;
-    const int row_in_tile = tid / LANES;
     const int stages = a.stages, cap = a.cap;
-    double   *sval = reinterpret_cast<double *>(dyn_smem);
-    unsigned *scol = reinterpret_cast<unsigned *>(dyn_smem + (size_t)stages * cap * sizeof(double));
+    // stage layout: [val cap*8][epi 4*PROW*8][col cap*4][ptr PROW*4]
+    const size_t stage_bytes = (size_t)cap * 12 + (size_t)PROW * 36;
     const int my_tiles = (a.ntiles > (int)blockIdx.x) ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int nvec = a.epi.nvec;
 
     if (tid == 0) {
-        for (int s = 0; s < stages; ++s) mbar_init(smem_u32(&bars[s]), 1u);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1u);
+            mbar_init(smem_u32(&empty_bar[s]), (unsigned)NCW);
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
-    // producer: thread 0 arms the stage's mbarrier with the byte count and fires two bulk copies
-    auto produce = [&](int i) {
-        const int t = (int)blockIdx.x + i * (int)gridDim.x, s = i % stages;
-        const unsigned p0 = a.tile_nz[t], p1 = a.tile_nz[t + 1];
-        const unsigned a0 = p0 & ~3u, cnt = ((p1 + 3u) & ~3u) - a0;       // 16-byte aligned window
-        const unsigned bar = smem_u32(&bars[s]);
-        mbar_arrive_expect_tx(bar, cnt * 12u);
-        if (cnt) {
-            tma_load_1d(smem_u32(sval + (size_t)s * cap), a.val + a0, cnt * 8u, bar);
-            tma_load_1d(smem_u32(scol + (size_t)s * cap), a.col + a0, cnt * 4u, bar);
-        }
-    };
-    if (tid == 0)
-        for (int i = 0; i < stages - 1 && i < my_tiles; ++i) produce(i);
-
-    // The matrix stream is already in flight; now make sure the peers' halo values of x have landed
-    // (the reference's MPI_Wait on the allgather, matrix.c:439).
-    if (a.wait_halo) {
-        if (tid < 32) {
-            const bool ok = halo_wait(a.kc.comm, a.kc.sc->halo_epoch);
-            if (!ok && tid == 0) a.kc.sc->error = 1;
-        }
-        __syncthreads();
-    }
-
     double dot[4] = {0.0, 0.0, 0.0, 0.0};
-    const double *__restrict__ x = a.x;
 
-    for (int i = 0; i < my_tiles; ++i) {
-        if (tid == 0 && i + stages - 1 < my_tiles) produce(i + stages - 1);
-
-        const int t = (int)blockIdx.x + i * (int)gridDim.x, s = i % stages;
-        const int row0 = a.tile_row[t], row1 = a.tile_row[t + 1];
-        const unsigned a0 = a.tile_nz[t] & ~3u;
-        const int row = row0 + row_in_tile;
-        const bool valid = row < row1;
-        unsigned pb = 0, pe = 0;
-        if (valid) { pb = a.ptr[row]; pe = a.ptr[row + 1]; }
-
-        mbar_wait(smem_u32(&bars[s]), (unsigned)(i / stages) & 1u);
-
-        const double   *sv = sval + (size_t)s * cap;
-        const unsigned *sc = scol + (size_t)s * cap;
-        double acc = 0.0;
-        int j = (int)(pb - a0) + lane;
-        const int e = (int)(pe - a0);
-        for (; j + 3 * LANES < e; j += 4 * LANES) {
-            const unsigned c0 = sc[j], c1 = sc[j + LANES], c2 = sc[j + 2 * LANES], c3 = sc[j + 3 * LANES];
-            const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-            const double v0 = sv[j], v1 = sv[j + LANES], v2 = sv[j + 2 * LANES], v3 = sv[j + 3 * LANES];
-            acc = fma(v0, x0, acc);
-            acc = fma(v1, x1, acc);
-            acc = fma(v2, x2, acc);
-            acc = fma(v3, x3, acc);
+    if (tid >= CTHREADS) {
+        // ===================================== producer warp ==========================================
+        if (tid == CTHREADS) {
+            for (int i = 0; i < my_tiles; ++i) {
+                const int t = (int)blockIdx.x + i * (int)gridDim.x, s = i % stages;
+                const int row0 = a.tile_row[t], row1 = a.tile_row[t + 1];
+                const unsigned p0 = a.tile_nz[t], p1 = a.tile_nz[t + 1];
+                const unsigned a0 = p0 & ~3u, cnt = ((p1 + 3u) & ~3u) - a0;          // 16-byte aligned windows
+                const int rowa = row0 & ~3, cntp = ((row1 + 1 + 3) & ~3) - rowa;
+                if (i >= stages) mbar_wait(smem_u32(&empty_bar[s]), (unsigned)(i / stages - 1) & 1u);
+                unsigned char *st = dyn_smem + (size_t)s * stage_bytes;
+                double   *sval = reinterpret_cast<double *>(st);
+                double   *sepi = sval + cap;
+                unsigned *scol = reinterpret_cast<unsigned *>(sepi + 4 * PROW);
+                unsigned *sptr = scol + cap;
+                hdr[s] = StageHdr{row0, row1, a0, rowa};
+                const unsigned bar = smem_u32(&full_bar[s]);
+                mbar_arrive_expect_tx(bar, cnt * 12u + (unsigned)cntp * 4u + (unsigned)(nvec * cntp) * 8u);
+                if (cnt) {
+                    tma_load_1d(smem_u32(sval), a.val + a0, cnt * 8u, bar);
+                    tma_load_1d(smem_u32(scol), a.col + a0, cnt * 4u, bar);
+                }
+                tma_load_1d(smem_u32(sptr), a.ptr + rowa, (unsigned)cntp * 4u, bar);
+                for (int v = 0; v < nvec; ++v)
+                    tma_load_1d(smem_u32(sepi + v * PROW), a.epi.vec[v] + rowa, (unsigned)cntp * 8u, bar);
+            }
         }
-        for (; j < e; j += LANES) acc = fma(sv[j], __ldg(x + sc[j]), acc);
+    } else {
+        // ===================================== consumer warps =========================================
+        // The matrix stream is already in flight; make sure the peers' halo values of x have landed before
+        // the first gather (the reference's MPI_Wait on the allgather, matrix.c:439).
+        if (a.wait_halo) {
+            if (tid < 32) {
+                const bool ok = halo_wait(a.kc.comm, a.kc.sc->halo_epoch);
+                if (!ok && tid == 0) a.kc.sc->error = 1;
+            }
+            named_bar_sync(1, CTHREADS);
+        }
+        const int lane = tid % LANES;
+        const int row_in_tile = tid / LANES;
+        const double *__restrict__ x = a.x;
+        const int ndot = a.epi.ndot;
 
-        acc = lanes_sum<LANES>(acc);
-        if (valid && lane == 0) row_epilogue(a, row, acc, dot);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int s = i % stages;
+            mbar_wait(smem_u32(&full_bar[s]), (unsigned)(i / stages) & 1u);
 
-        __syncthreads();     // every thread is done with stage s -> the producer may refill it
+            const unsigned char *st = dyn_smem + (size_t)s * stage_bytes;
+            const double   *sval = reinterpret_cast<const double *>(st);
+            const double   *sepi = sval + cap;
+            const unsigned *scol = reinterpret_cast<const unsigned *>(sepi + 4 * PROW);
+            const unsigned *sptr = scol + cap;
+            const StageHdr h = hdr[s];
+            const int row = h.row0 + row_in_tile;
+            const bool valid = row < h.row1;
+            int j = 0, e = 0;
+            if (valid) {
+                j = (int)(sptr[row - h.rowa] - h.a0) + lane;
+                e = (int)(sptr[row - h.rowa + 1] - h.a0);
+            }
+            double acc = 0.0;
+            while (j < e) {                                   // UNR gathers in flight, summed in order
+                unsigned c[UNR];
+                double v[UNR], xv[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    // clamp instead of predicating: unconditional loads batch freely (a predicated load per
+                    // slot runs out of predicate registers after 7); the FMA below is what is predicated
+                    const int idx = min(j + u * LANES, e - 1);
+                    c[u] = scol[idx];
+                    v[u] = sval[idx];
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+                    if (j + u * LANES < e) acc = fma(v[u], xv[u], acc);
+                j += UNR * LANES;
+            }
+            acc = lanes_sum<LANES>(acc);
+            if (valid && lane == 0) {
+                a.y[row] = acc;
+                const int ro = row - h.rowa;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < ndot) {
+                        const double av = a.epi.ia[k] >= 0 ? sepi[a.epi.ia[k] * PROW + ro] : acc;
+                        const double bv = a.epi.ib[k] >= 0 ? sepi[a.epi.ib[k] * PROW + ro] : acc;
+                        dot[k] = fma(av, bv, dot[k]);
+                    }
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[s]));   // this warp is done with stage s
+        }
     }
 
     if (!needs_tail(a.kc)) return;
@@ -161,6 +208,7 @@ __global__ void __launch_bounds__(256) spmv_rowsplit_kernel(const __grid_constan
     const double *__restrict__ x = a.x;
     const double *__restrict__ val = a.val;
     const unsigned *__restrict__ col = a.col;
+    const int ndot = a.epi.ndot;
     double dot[4] = {0.0, 0.0, 0.0, 0.0};
     for (long long base = (long long)blockIdx.x * RPB; base < a.rows; base += (long long)gridDim.x * RPB) {
         const int row = (int)base + tid / LANES;
@@ -179,26 +227,36 @@ __global__ void __launch_bounds__(256) spmv_rowsplit_kernel(const __grid_constan
         }
         for (; j < pe; j += LANES) acc = fma(val[j], __ldg(x + col[j]), acc);
         acc = lanes_sum<LANES>(acc);
-        if (valid && lane == 0) row_epilogue(a, row, acc, dot);
+        if (valid && lane == 0) {
+            a.y[row] = acc;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < ndot) {
+                    const double av = a.epi.ia[k] >= 0 ? a.epi.vec[a.epi.ia[k]][row] : acc;
+                    const double bv = a.epi.ib[k] >= 0 ? a.epi.vec[a.epi.ib[k]][row] : acc;
+                    dot[k] = fma(av, bv, dot[k]);
+                }
+            }
+        }
     }
     if (!needs_tail(a.kc)) return;
     block_sum<4>(dot, scratch);
     kernel_tail<4>(a.kc, dot, scratch);
 }
 
-template <int LANES, int THREADS>
-cudaError_t launch_tma(int grid, size_t smem, const SpmvArgs &a, cudaStream_t st)
+template <int LANES, int CTHREADS>
+cudaError_t launch_ws(int grid, size_t smem, const SpmvArgs &a, cudaStream_t st)
 {
-    spmv_tma_kernel<LANES, THREADS><<<grid, THREADS, smem, st>>>(a);
+    spmv_ws_kernel<LANES, CTHREADS><<<grid, CTHREADS + 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 template <int LANES>
-cudaError_t launch_tma_t(int threads, int grid, size_t smem, const SpmvArgs &a, cudaStream_t st)
+cudaError_t launch_ws_t(int threads, int grid, size_t smem, const SpmvArgs &a, cudaStream_t st)
 {
     switch (threads) {
-    case 128: return launch_tma<LANES, 128>(grid, smem, a, st);
-    case 256: return launch_tma<LANES, 256>(grid, smem, a, st);
-    case 512: return launch_tma<LANES, 512>(grid, smem, a, st);
+    case 128: return launch_ws<LANES, 128>(grid, smem, a, st);
+    case 256: return launch_ws<LANES, 256>(grid, smem, a, st);
+    case 512: return launch_ws<LANES, 512>(grid, smem, a, st);
     default:  return cudaErrorInvalidValue;
     }
 }
@@ -209,14 +267,14 @@ cudaError_t launch_rowsplit(int grid, const SpmvArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int LANES, int THREADS>
+template <int LANES, int CTHREADS>
 cudaError_t set_attr()
 {
     // opt-in limit is 227 KB per CTA *including* the kernel's static shared memory
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, spmv_tma_kernel<LANES, THREADS>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, spmv_ws_kernel<LANES, CTHREADS>);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(spmv_tma_kernel<LANES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(spmv_ws_kernel<LANES, CTHREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 227 * 1024 - (int)fa.sharedSizeBytes);
 }
 template <int LANES>
@@ -230,7 +288,24 @@ cudaError_t set_attr_l()
 
 } // namespace
 
-size_t spmv_tma_smem_bytes(int cap, int stages) { return (size_t)stages * (size_t)cap * 12u; }
+size_t spmv_tma_smem_bytes(int cap, int stages, int threads, int lanes)
+{
+    const size_t prow = (size_t)(threads / lanes + PROW_PAD);
+    return (size_t)stages * ((size_t)cap * 12u + prow * 36u);
+}
+
+void epi_add_dot(EpiArgs &e, const double *a, const double *b)
+{
+    auto index_of = [&](const double *p) -> int {
+        if (!p) return -1;
+        for (int i = 0; i < e.nvec; ++i) if (e.vec[i] == p) return i;
+        e.vec[e.nvec] = p;
+        return e.nvec++;
+    };
+    e.ia[e.ndot] = index_of(a);
+    e.ib[e.ndot] = index_of(b);
+    ++e.ndot;
+}
 
 int spmv_setup_attributes()
 {
@@ -248,12 +323,12 @@ int launch_spmv(int kind, int lanes, int threads, int grid, size_t smem, const S
 {
     if (kind == 0) {
         switch (lanes) {
-        case 1:  return (int)launch_tma_t<1>(threads, grid, smem, a, st);
-        case 2:  return (int)launch_tma_t<2>(threads, grid, smem, a, st);
-        case 4:  return (int)launch_tma_t<4>(threads, grid, smem, a, st);
-        case 8:  return (int)launch_tma_t<8>(threads, grid, smem, a, st);
-        case 16: return (int)launch_tma_t<16>(threads, grid, smem, a, st);
-        case 32: return (int)launch_tma_t<32>(threads, grid, smem, a, st);
+        case 1:  return (int)launch_ws_t<1>(threads, grid, smem, a, st);
+        case 2:  return (int)launch_ws_t<2>(threads, grid, smem, a, st);
+        case 4:  return (int)launch_ws_t<4>(threads, grid, smem, a, st);
+        case 8:  return (int)launch_ws_t<8>(threads, grid, smem, a, st);
+        case 16: return (int)launch_ws_t<16>(threads, grid, smem, a, st);
+        case 32: return (int)launch_ws_t<32>(threads, grid, smem, a, st);
         default: return (int)cudaErrorInvalidValue;
         }
     }

@@ -4,11 +4,13 @@
 
 namespace bicg {
 
-// dots fused into the SpMV epilogue: dot[k] += A_k[row] * B_k[row]; a null pointer means "the y just computed"
+// dots fused into the SpMV epilogue: dot[k] += U[row] * V[row] where U, V are either one of up to four
+// epilogue vectors (index into vec[]) or the y just computed (index -1)
 struct EpiArgs {
+    int nvec;
+    const double *vec[4];
     int ndot;
-    const double *a[4];
-    const double *b[4];
+    int ia[4], ib[4];
 };
 
 struct SpmvArgs {
@@ -32,11 +34,13 @@ struct SpmvArgs {
     int wait_halo;              // 1: x's ghost part is filled by peers; wait for their halo flags first
 };
 
-// kind 0: TMA-staged tile kernel, kind 1: row-split kernel.  threads only matters for kind 0.
+// kind 0: warp-specialised TMA tile kernel, kind 1: row-split kernel.  threads (consumer threads) only matters for kind 0.
 // Returns cudaError_t as int.
 int launch_spmv(int kind, int lanes, int threads, int grid, size_t smem_bytes, const SpmvArgs &a, cudaStream_t st);
 // one-time opt-in to > 48 KB dynamic shared memory for every instantiation
 int spmv_setup_attributes();
-size_t spmv_tma_smem_bytes(int cap, int stages);
+size_t spmv_tma_smem_bytes(int cap, int stages, int threads, int lanes);
+// add a dot term (a . b) to an epilogue; null pointer = the y just computed
+void epi_add_dot(EpiArgs &e, const double *a, const double *b);
 
 } // namespace bicg

@@ -33,11 +33,22 @@ template <> __device__ __forceinline__ Pk<2> ld<2>(const double *p, int i)
     const double2 t = *reinterpret_cast<const double2 *>(p + i);
     Pk<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
 }
+template <> __device__ __forceinline__ Pk<4> ld<4>(const double *p, int i)
+{
+    const double2 t = *reinterpret_cast<const double2 *>(p + i);
+    const double2 u = *reinterpret_cast<const double2 *>(p + i + 2);
+    Pk<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = u.x; r.v[3] = u.y; return r;
+}
 template <int W> __device__ __forceinline__ void st(double *p, int i, const Pk<W> &a);
 template <> __device__ __forceinline__ void st<1>(double *p, int i, const Pk<1> &a) { p[i] = a.v[0]; }
 template <> __device__ __forceinline__ void st<2>(double *p, int i, const Pk<2> &a)
 {
     *reinterpret_cast<double2 *>(p + i) = make_double2(a.v[0], a.v[1]);
+}
+template <> __device__ __forceinline__ void st<4>(double *p, int i, const Pk<4> &a)
+{
+    *reinterpret_cast<double2 *>(p + i) = make_double2(a.v[0], a.v[1]);
+    *reinterpret_cast<double2 *>(p + i + 2) = make_double2(a.v[2], a.v[3]);
 }
 
 __host__ __device__ constexpr int phase_ndot(int ph)
@@ -222,9 +233,11 @@ __global__ void __launch_bounds__(256) vec_kernel(const __grid_constant__ VecArg
     for (int k = 0; k < NDA; ++k) dot[k] = 0.0;
 
     if constexpr (PH != PH_PUSH) {
-        int i = lo + 2 * (int)threadIdx.x;
-        for (; i + 1 < hi; i += 2 * (int)blockDim.x) body<PH, 2>(a.v, i, c, dot);
-        if (i < hi) body<PH, 1>(a.v, i, c, dot);          // odd tail element of the last chunk
+        // 4 doubles (two 16-byte loads per vector) per thread and step: twice the bytes in flight of a
+        // double2 loop; lo is a multiple of 4 and every vector is 128-byte aligned
+        int i = lo + 4 * (int)threadIdx.x;
+        for (; i + 3 < hi; i += 4 * (int)blockDim.x) body<PH, 4>(a.v, i, c, dot);
+        for (; i < hi; ++i) body<PH, 1>(a.v, i, c, dot);  // < 4 trailing elements of the last chunk (one thread)
     }
 
     const bool pushing = a.push.npeers > 0;

@@ -24,7 +24,7 @@ struct VecArgs {
     KernelCommon kc;
     VecPtrs v;
     int n;          // local length
-    int chunk;      // elements per CTA (even)
+    int chunk;      // elements per CTA (multiple of 4)
     PushDesc push;
 };
 

@@ -153,7 +153,6 @@ def ref_solve(method, n, ptr, col, val, b, x0=None, tol=1e-15, max_iter=1000, kr
     r = np.array(b, dtype=np.float64)
     L.orc_ref_config(tol, max_iter, 1, 1)
     L.orc_ref_hist_reset()
-    os.environ.setdefault("MALLOC_MMAP_THRESHOLD_", "0")
     args = [C.byref(D), C.byref(O), C.byref(info), _p(x, _dp), _p(r, _dp)]
     if method == "pipe_bicgstab_rr":
         it = L.pipe_bicgstab_rr(*args, krr, nrr)

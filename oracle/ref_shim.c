@@ -47,6 +47,8 @@ int orc_ref_total_iter(void) { return g_titer; }
 double orc_ref_total_time(void) { return g_ttime; }
 double orc_ref_avg_time(void) { return g_atime; }
 
+void *orc_ref_zmalloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
+
 int orc_ref_printf(const char *fmt, ...)
 {
     va_list ap, aq;

@@ -1,0 +1,158 @@
+"""CPU: the C-ABI library loads, exports every symbol include/bicgstab_b200.h declares, and its host-only entry
+points (planning, generators, Matrix-Market loader) work without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "bicgstab_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"typedef[^;]*;", "", txt)                       # function-pointer typedefs are not symbols
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", txt))
+    return {n for n in names if not n.startswith("bicg_allgather_fn") and n not in ("defined",)}
+
+
+def test_every_declared_symbol_is_exported(B):
+    declared = _declared_symbols()
+    assert {"bicgstab", "ca_bicgstab", "pipe_bicgstab", "pipe_bicgstab_rr", "MPI_csr_spmv_ovlap",
+            "MPI_csr_load_matrix_block", "csr_init_matrix", "csr_free_matrix"} <= declared
+    out = subprocess.run(["nm", "-D", "--defined-only", B.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    missing = sorted(declared - exported)
+    assert not missing, f"declared in include/bicgstab_b200.h but not exported: {missing}"
+    assert declared <= set(B.SYMBOLS) | {"bicg_plan_push_runs"}, sorted(declared - set(B.SYMBOLS))
+
+
+def test_struct_layouts_match_reference(B):
+    # matrix.h:19-26 / 28-33
+    assert C.sizeof(B.CSR_Matrix) == 40
+    assert [getattr(B.CSR_Matrix, f).offset for f in ("val", "col", "ptr", "nz", "rows", "cols")] == [0, 8, 16, 24, 28, 32]
+    assert C.sizeof(B.INFO_Matrix) == 32
+    assert [getattr(B.INFO_Matrix, f).offset for f in ("nz", "rows", "cols", "code", "recvcounts", "displs")] == [0, 4, 8, 12, 16, 24]
+
+
+def test_sass_is_blackwell_native(B):
+    """The shipped cubin is sm_100a and the SpMV really uses the TMA bulk-copy path (UBLKCP) + mbarriers."""
+    out = subprocess.run(["cuobjdump", "-lelf", B.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out.stdout
+    sass = subprocess.run(["cuobjdump", "-sass", B.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS" in sass and "DFMA" in sass
+
+
+@pytest.mark.parametrize("n,world", [(10, 3), (1601613, 8), (7, 8), (16, 4)])
+def test_partition_rule(B, O, n, world):
+    cnt, dsp = B.plan_partition(n, world)
+    c2, d2 = O.partition(n, world)                              # oracle restatement of matrix.c:295-308
+    assert np.array_equal(cnt, c2) and np.array_equal(dsp, d2)
+    assert cnt.sum() == n and dsp[0] == 0 and np.all(np.diff(dsp) == cnt[:-1])
+    assert cnt.max() - cnt.min() <= 1 and np.all(np.diff(cnt) <= 0)
+
+
+def test_tile_plan_covers_rows(B):
+    blk = B.gen_block("stencil15", 13, 14.0)
+    _, _, ptr = blk.diag_arrays()
+    rows = blk.n_loc
+    for rpt, cap in ((256, 4000), (128, 1000), (32, 64)):
+        tr = (C.c_int * (rows + 2))()
+        nt = B.lib.bicg_plan_tiles(ptr.ctypes.data_as(C.POINTER(C.c_uint)), rows, rpt, cap, tr, rows + 2)
+        t = np.array(tr[:nt + 1])
+        assert t[0] == 0 and t[-1] == rows and np.all(np.diff(t) > 0) and np.all(np.diff(t) <= rpt)
+        assert np.all(ptr[t[1:]].astype(np.int64) - ptr[t[:-1]].astype(np.int64) <= cap)
+    tr = (C.c_int * (rows + 2))()
+    assert B.lib.bicg_plan_tiles(ptr.ctypes.data_as(C.POINTER(C.c_uint)), rows, 32, 5, tr, rows + 2) == -2   # a row > cap
+
+
+def test_generators_match_block_split_of_global(B):
+    """gen_block(rank, world) must equal the reference-style split of the world=1 matrix (matrix.c:380-392)."""
+    g1 = B.gen_block("stencil15", 8, 14.0)
+    ptr, col, val = B.block_to_global_csr(g1)
+    for world in (2, 3):
+        for rank in range(world):
+            a = B.gen_block("stencil15", 8, 14.0, rank=rank, world=world)
+            b = B.blocks_from_csr(g1.n, ptr, col, val, rank, world)
+            for x, y in ((a.diag_arrays(), b.diag_arrays()), (a.offd_arrays(), b.offd_arrays())):
+                for u, v in zip(x, y):
+                    assert np.array_equal(np.asarray(u), np.asarray(v))
+            assert np.array_equal(a.recvcounts, b.recvcounts) and np.array_equal(a.displs, b.displs)
+            assert a.diag.cols == a.n_loc and a.offd.cols == g1.n                 # matrix.c:344, 351
+
+
+def test_matrix_market_loader(B, O, tmp_path):
+    """MPI_csr_load_matrix_block: same blocks as the reference's loader (checked via the compiled reference when
+    present, else via the generator the file was written from); in-row order = file order (stable row sort)."""
+    blk = B.gen_block("convdiff", 12, 1.5)
+    n = blk.n
+    ptr, col, val = B.block_to_global_csr(blk)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val, col, ptr), shape=(n, n)).tocsc().tocoo()          # column-major like SuiteSparse files
+    f = tmp_path / "a.mtx"
+    with open(f, "w") as fh:
+        fh.write("%%MatrixMarket matrix coordinate real general\n% comment\n\n")
+        fh.write(f"{n} {n} {A.nnz}\n")
+        for r, c, v in zip(A.row, A.col, A.data):
+            fh.write(f"{r + 1} {c + 1} {float(v)!r}\n")
+    got = B.load_matrix_block(f, world=1)
+    assert (got.n, got.n_loc, int(got.info.nz)) == (n, n, A.nnz) and got.info.code == b"MCRG"
+    for u, v in zip(got.diag_arrays(), blk.diag_arrays()):
+        assert np.array_equal(np.asarray(u), np.asarray(v))
+    assert got.offd.nz == 0 and got.offd.rows == n and got.offd.cols == n
+    ref_main = os.path.join(ROOT, "oracle", "_ref", "ref_main_hist")
+    if os.path.exists(ref_main):
+        # the reference program itself (main.c unchanged) on the same file: same iteration count as the oracle
+        env = dict(os.environ, REF_EPS="1e-10", REF_MAX_ITER="500", REF_OUT_ITER="1", MALLOC_MMAP_THRESHOLD_="0")
+        out = subprocess.run([ref_main, str(f), "bicgstab"], env=env, capture_output=True, text=True, check=True).stdout
+        it_ref = int(re.search(r"Total iter\s*:\s*(\d+)", out).group(1))
+        b = O.spmv(n, ptr, col, val, np.ones(n))
+        assert O.solve("bicgstab", n, ptr, col, val, b, tol=1e-10, max_iter=500)["iters"] == it_ref
+
+
+def test_matrix_market_pattern_and_errors(B, tmp_path):
+    f = tmp_path / "p.mtx"
+    f.write_text("%%MatrixMarket matrix coordinate pattern general\n3 3 4\n1 1\n2 2\n3 3\n1 3\n")
+    got = B.load_matrix_block(f, world=1)
+    val, col, ptr = got.diag_arrays()
+    assert list(ptr) == [0, 2, 3, 4] and list(col) == [0, 2, 1, 2] and np.all(np.asarray(val) == 1.0)
+    bad = tmp_path / "bad.mtx"
+    bad.write_text("not a banner\n")
+    code = ("import sys; sys.path.insert(0, %r); import mpi_bicgstab_b200 as B; B.load_matrix_block(%r, world=1)"
+            % (ROOT, str(bad)))
+    p = subprocess.run(["python", "-c", code], capture_output=True, text=True)
+    assert p.returncode != 0 and "Could not process Matrix Market banner" in p.stderr        # matrix.c:281-284
+
+
+def test_compute_entry_points_fail_loudly_without_gpu(B):
+    """No CPU fallback: on a box without a usable GPU a solve must exit(1) with a message, not return numbers."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np; import mpi_bicgstab_b200 as B; "
+            "blk = B.gen_block('laplace5', 8); x = np.zeros(blk.n); b = np.ones(blk.n); B.bicgstab(blk, x, b); print('RETURNED')" % ROOT)
+    p = subprocess.run(["python", "-c", code], capture_output=True, text=True)
+    assert p.returncode == 1 and "RETURNED" not in p.stdout and "no usable CUDA device" in p.stderr
+
+
+def test_reference_main_c_links_against_the_library(B, tmp_path):
+    """The drop-in claim itself: the reference's main.c, UNCHANGED, compiles against include/compat/mpi.h and
+    links against libbicgstab_b200.so (needs /root/reference, so only in the build container)."""
+    src = "/root/reference/src/main.c"
+    if not os.path.exists(src):
+        pytest.skip("/root/reference not present")
+    exe = tmp_path / "solver"
+    cmd = ["gcc", "-O2", "-w", "-I" + os.path.join(ROOT, "include", "compat"), "-I/root/reference/src", src,
+           "-L" + os.path.dirname(B.LIB_PATH), "-lbicgstab_b200", "-Wl,-rpath," + os.path.dirname(B.LIB_PATH), "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)         # no arguments -> usage text (main.c:64-75)
+    assert "Usage:" in p.stdout and "pipe_bicgstab_rr" in p.stdout
+    undefined = subprocess.run(["nm", "-u", str(exe)], capture_output=True, text=True).stdout
+    for sym in ("bicgstab", "ca_bicgstab", "pipe_bicgstab", "pipe_bicgstab_rr", "MPI_csr_spmv_ovlap",
+                "MPI_csr_load_matrix_block", "csr_init_matrix", "csr_free_matrix"):
+        assert re.search(r"\bU %s\b" % sym, undefined), sym
