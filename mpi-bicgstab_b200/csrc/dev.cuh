@@ -301,7 +301,7 @@ __device__ __forceinline__ void finalize(int fin, Scalars *s, double *hist, cons
 // ------------------------------------------------------------------------------------------------
 // `local` holds this CTA's dots (valid in warp 0 after block_sum).  `scratch`: >= 32*MAX_DOTS doubles.
 // Every thread of the CTA must call this.  All global writes of the CTA that the tail's signals cover
-// (halo pushes) must have been fenced (__threadfence_system) by their writers before the call.
+// (halo pushes) are ordered by the CTA barrier + thread 0's system-scope fence at the top of this function.
 template <int NDOT>
 __device__ __forceinline__ void kernel_tail(const KernelCommon &kc, double (&local)[NDOT > 0 ? NDOT : 1],
                                             double *scratch)
@@ -309,10 +309,12 @@ __device__ __forceinline__ void kernel_tail(const KernelCommon &kc, double (&loc
     __shared__ int s_last;
     Scalars *sc = kc.sc;
     const int tid = threadIdx.x;
+    __syncthreads();                     // every thread's global / peer stores of this CTA happen-before the fence
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < NDOT; ++k) __stcg(&kc.partials[(size_t)blockIdx.x * MAX_DOTS + k], local[k]);
-        __threadfence();
+        if (kc.tail.signal_halo) __threadfence_system();   // peer (NVLink) stores of the halo push
+        else __threadfence();
         const unsigned t = atomicAdd(&sc->ticket, 1u);
         s_last = (t == gridDim.x - 1);
     }

@@ -40,6 +40,7 @@ struct Config {
     int device = -1;
     int halo_gap = 64;
     int verbose = 0;
+    int fence_writers = 1;       // halo push: writer threads fence their own peer stores (belt and braces)
 };
 
 struct TuneKey {

@@ -71,6 +71,7 @@ struct Seq {
         if (push_vec >= 0 && m->world > 1) {
             a.kc.tail.signal_halo = 1;               // every rank advances its halo epoch, senders also signal
             a.push.npeers = m->npush;
+            a.push.fence_writers = c.cfg.fence_writers;
             a.push.src = m->vec(push_vec);
             for (int s = 0; s < m->npush; ++s) {
                 const int d = m->push_peer[s];

@@ -196,6 +196,7 @@ __device__ __forceinline__ void body(const VecPtrs &v, int i, const Coef &c, dou
 // copy the parts of this CTA's chunk [lo, hi) that peers need into their ghost regions (peer stores)
 __device__ __forceinline__ void push_chunk(const PushDesc &pd, int lo, int hi)
 {
+    bool stored = false;
     for (int pi = 0; pi < pd.npeers; ++pi) {
         const PushRun *runs = pd.runs[pi];
         const int nr = pd.nruns[pi];
@@ -209,9 +210,12 @@ __device__ __forceinline__ void push_chunk(const PushDesc &pd, int lo, int hi)
             if (r.src >= hi) break;
             const int s = max(r.src, lo), e = min(r.src + r.len, hi);
             double *d = pd.dst[pi] + ((long long)r.dst_off - (long long)r.src);
-            for (int i = s + (int)threadIdx.x; i < e; i += (int)blockDim.x) d[i] = __ldcg(pd.src + i);
+            for (int i = s + (int)threadIdx.x; i < e; i += (int)blockDim.x) { d[i] = __ldcg(pd.src + i); stored = true; }
         }
     }
+    // a thread that wrote to a peer orders its own NVLink stores before anything that follows (the halo flag
+    // is released by the tail after a CTA barrier, a grid-wide ticket and another system fence)
+    if (stored && pd.fence_writers) __threadfence_system();
 }
 
 template <int PH>
@@ -244,7 +248,9 @@ __global__ void __launch_bounds__(256) vec_kernel(const __grid_constant__ VecArg
     if (pushing) {
         __syncthreads();                 // this CTA's elements are final
         push_chunk(a.push, lo, hi);
-        __threadfence_system();          // peer stores ordered before the tail's flag
+        // the peer stores are ordered before the halo flag by ONE system-scope fence per CTA: kernel_tail's
+        // thread 0 fences after the __syncthreads that follows (cumulativity covers the whole CTA's stores);
+        // a fence.sys in every thread costs microseconds per kernel
     }
     if (ND == 0 && a.kc.tail.op == TAIL_NONE && !a.kc.tail.signal_halo) return;
     if (ND > 0) block_sum<NDA>(dot, scratch);
