@@ -38,12 +38,11 @@ struct Scalars {
     unsigned int pad_;
 };
 
-// one mailbox = what rank `src` contributes to one reduction; 128 B so that no two share a line
-struct alignas(128) Mailbox {
-    double v[MAIL_VALS];
-    unsigned long long flag;     // epoch of the reduction the values belong to
-    unsigned long long pad_[7];
-};
+// one mailbox = what rank `src` contributes to one reduction: eight 16-byte slots {value, epoch}.  A slot is written
+// with ONE 16-byte store, so value and epoch arrive together and the receiver needs no fence between "flag" and
+// data (the LL idea of NCCL); 128 B so that no two mailboxes share a line.
+struct alignas(16) LLSlot { double v; unsigned long long ep; };
+struct alignas(128) Mailbox { LLSlot s[MAIL_VALS]; };
 struct alignas(128) HaloFlag { unsigned long long epoch; unsigned long long pad_[15]; };
 
 // peer-memory view of the job, passed by value to every kernel
@@ -143,6 +142,26 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_ll(LLSlot *p, double v, unsigned long long ep)
+{
+    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(ep) : "memory");
+}
+__device__ __forceinline__ void ld_ll(const LLSlot *p, double &v, unsigned long long &ep)
+{
+    long long vb;
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(vb), "=l"(ep) : "l"(p) : "memory");
+    v = __longlong_as_double(vb);
+}
 __device__ __forceinline__ double ld_volatile_f64(const double *p)
 {
     double v;
@@ -194,35 +213,45 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double *scratch)
 // ------------------------------------------------------------------------------------------------
 // cross-GPU reduction over peer mailboxes (called by warp 0 of the last CTA, all 32 lanes)
 // ------------------------------------------------------------------------------------------------
-// post: lane p stores this rank's `nv` values into rank p's mailbox[parity][me] and releases the flag.
+// post: lane p stores this rank's `nv` values (at least one slot, so a pure barrier works too) into rank p's
+// mailbox[parity][me], each as one {value, epoch} store.
 __device__ __forceinline__ void xg_post(const CommDev &c, unsigned epoch, const double *vals, int nv)
 {
     const int lane = threadIdx.x & 31;
     if (lane < c.world) {
         Mailbox *mb = c.mail[lane] + (epoch & 1u) * MAX_RANKS + c.rank;
-        for (int k = 0; k < nv; ++k) mb->v[k] = vals[k];
-        __threadfence_system();
-        st_release_sys(&mb->flag, (unsigned long long)epoch);
+        const int n = nv > 0 ? nv : 1;
+        for (int k = 0; k < n; ++k) st_ll(&mb->s[k], nv > 0 ? vals[k] : 0.0, (unsigned long long)epoch);
     }
     __syncwarp();
 }
-// wait: lane p polls its own rank's mailbox[parity][p]; then lane k sums value k over ranks 0..world-1
-// in rank order (the same order on every rank -> identical results everywhere).  Returns false on timeout.
+// wait: lane p polls the slots rank p sent to this rank until they carry `epoch`, keeps rank p's values; lane k
+// then adds value k over ranks 0..world-1 in rank order (the same order on every rank -> bitwise identical
+// results everywhere).  Returns false on timeout.
 __device__ __forceinline__ bool xg_wait_sum(const CommDev &c, unsigned epoch, double *vals, int nv)
 {
+    __shared__ double s_contrib[MAX_RANKS][MAIL_VALS];
     const int lane = threadIdx.x & 31;
     const Mailbox *mine = c.mail[c.rank] + (epoch & 1u) * MAX_RANKS;
     bool ok = true;
     if (lane < c.world) {
         const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_sys(&mine[lane].flag) < (unsigned long long)epoch) {
-            if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
+        const int n = nv > 0 ? nv : 1;
+        for (int k = 0; k < n && ok; ++k) {
+            double v; unsigned long long ep;
+            for (;;) {
+                ld_ll(&mine[lane].s[k], v, ep);
+                if (ep >= (unsigned long long)epoch) break;
+                if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
+            }
+            s_contrib[lane][k] = v;
         }
     }
     ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
     if (ok && lane < nv) {
-        double acc = ld_volatile_f64(&mine[0].v[lane]);
-        for (int p = 1; p < c.world; ++p) acc += ld_volatile_f64(&mine[p].v[lane]);
+        double acc = s_contrib[0][lane];
+        for (int p = 1; p < c.world; ++p) acc += s_contrib[p][lane];
         vals[lane] = acc;
     }
     __syncwarp();
@@ -296,45 +325,31 @@ __device__ __forceinline__ void finalize(int fin, Scalars *s, double *hist, cons
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// kernel tail: elect the last CTA, combine the grid's partial dots in a fixed order, run the TailDesc
-// ------------------------------------------------------------------------------------------------
-// `local` holds this CTA's dots (valid in warp 0 after block_sum).  `scratch`: >= 32*MAX_DOTS doubles.
-// Every thread of the CTA must call this.  All global writes of the CTA that the tail's signals cover
-// (halo pushes) are ordered by the CTA barrier + thread 0's system-scope fence at the top of this function.
-template <int NDOT>
-__device__ __forceinline__ void kernel_tail(const KernelCommon &kc, double (&local)[NDOT > 0 ? NDOT : 1],
-                                            double *scratch)
+// Wait until every peer in recv_mask has published halo epoch >= `expect` (called by warp 0 of a CTA).
+__device__ __forceinline__ bool halo_wait_epoch(const CommDev &c, unsigned expect)
 {
-    __shared__ int s_last;
-    Scalars *sc = kc.sc;
-    const int tid = threadIdx.x;
-    __syncthreads();                     // every thread's global / peer stores of this CTA happen-before the fence
-    if (tid == 0) {
-#pragma unroll
-        for (int k = 0; k < NDOT; ++k) __stcg(&kc.partials[(size_t)blockIdx.x * MAX_DOTS + k], local[k]);
-        if (kc.tail.signal_halo) __threadfence_system();   // peer (NVLink) stores of the halo push
-        else __threadfence();
-        const unsigned t = atomicAdd(&sc->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-
-    // grid-level combination: thread t sums CTAs t, t+T, ... ascending, then a fixed CTA tree
-    double tot[NDOT > 0 ? NDOT : 1];
-#pragma unroll
-    for (int k = 0; k < (NDOT > 0 ? NDOT : 1); ++k) tot[k] = 0.0;
-    if (NDOT > 0) {
-        for (unsigned b = tid; b < gridDim.x; b += blockDim.x) {
-#pragma unroll
-            for (int k = 0; k < NDOT; ++k) tot[k] += __ldcg(&kc.partials[(size_t)b * MAX_DOTS + k]);
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+    if (lane < c.world && ((c.recv_mask >> lane) & 1u)) {
+        const unsigned long long *f = &c.hflag[c.rank][lane].epoch;
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(f) < (unsigned long long)expect) {
+            if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
         }
-        block_sum<(NDOT > 0 ? NDOT : 1)>(tot, scratch);
     }
-    if (tid >= 32) return;                       // warp 0 finishes the job
+    return __all_sync(0xffffffffu, ok);
+}
 
+__device__ __forceinline__ bool halo_wait(const CommDev &c, unsigned expect) { return halo_wait_epoch(c, expect); }
+
+// What the elected warp does once the grid's dots are combined: `tot` holds the totals in every lane.
+// Runs the TailDesc (cross-GPU reduction over the peer mailboxes, scalar recurrence, halo-ready signal) and, when
+// wait_halo is set (persistent kernel), also waits for the peers' halo signal of the same epoch.
+template <int NDOT>
+__device__ __forceinline__ void tail_warp(const KernelCommon &kc, double (&tot)[NDOT > 0 ? NDOT : 1], bool wait_halo)
+{
+    Scalars *sc = kc.sc;
+    const int tid = threadIdx.x & 31;
     __shared__ double s_vals[MAIL_VALS];
     const TailDesc &td = kc.tail;
     const int lane = tid;
@@ -388,24 +403,52 @@ __device__ __forceinline__ void kernel_tail(const KernelCommon &kc, double (&loc
         if (lane < kc.comm.world && ((kc.comm.send_mask >> lane) & 1u))
             st_release_sys(&kc.comm.hflag[lane][kc.comm.rank].epoch, (unsigned long long)he);
         __syncwarp();
+        if (wait_halo && !halo_wait_epoch(kc.comm, he) && lane == 0) { sc->error = 1; sc->done = 1; }
         if (lane == 0) sc->halo_epoch = he;
     }
-    if (lane == 0) { __threadfence(); sc->ticket = 0u; }
 }
 
-// Wait until every peer in recv_mask has published halo epoch >= `expect` (called by warp 0 of a CTA).
-__device__ __forceinline__ bool halo_wait(const CommDev &c, unsigned expect)
+
+// ------------------------------------------------------------------------------------------------
+// kernel tail: elect the last CTA, combine the grid's partial dots in a fixed order, run the TailDesc
+// ------------------------------------------------------------------------------------------------
+// `local` holds this CTA's dots (valid in warp 0 after block_sum).  `scratch`: >= 32*MAX_DOTS doubles.
+// Every thread of the CTA must call this.  All global writes of the CTA that the tail's signals cover
+// (halo pushes) are ordered by the CTA barrier + thread 0's system-scope fence at the top of this function.
+template <int NDOT>
+__device__ __forceinline__ void kernel_tail(const KernelCommon &kc, double (&local)[NDOT > 0 ? NDOT : 1],
+                                            double *scratch)
 {
-    const int lane = threadIdx.x & 31;
-    bool ok = true;
-    if (lane < c.world && ((c.recv_mask >> lane) & 1u)) {
-        const unsigned long long *f = &c.hflag[c.rank][lane].epoch;
-        const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_sys(f) < (unsigned long long)expect) {
-            if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
-        }
+    __shared__ int s_last;
+    Scalars *sc = kc.sc;
+    const int tid = threadIdx.x;
+    __syncthreads();                     // every thread's global / peer stores of this CTA happen-before the fence
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NDOT; ++k) __stcg(&kc.partials[(size_t)blockIdx.x * MAX_DOTS + k], local[k]);
+        if (kc.tail.signal_halo) __threadfence_system();   // peer (NVLink) stores of the halo push
+        else __threadfence();
+        const unsigned t = atomicAdd(&sc->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
     }
-    return __all_sync(0xffffffffu, ok);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+
+    // grid-level combination: thread t sums CTAs t, t+T, ... ascending, then a fixed CTA tree
+    double tot[NDOT > 0 ? NDOT : 1];
+#pragma unroll
+    for (int k = 0; k < (NDOT > 0 ? NDOT : 1); ++k) tot[k] = 0.0;
+    if (NDOT > 0) {
+        for (unsigned b = tid; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+            for (int k = 0; k < NDOT; ++k) tot[k] += __ldcg(&kc.partials[(size_t)b * MAX_DOTS + k]);
+        }
+        block_sum<(NDOT > 0 ? NDOT : 1)>(tot, scratch);
+    }
+    if (tid >= 32) return;                       // warp 0 finishes the job
+    tail_warp<NDOT>(kc, tot, false);
+    if (tid == 0) { __threadfence(); sc->ticket = 0u; }
 }
 
 } // namespace bicg

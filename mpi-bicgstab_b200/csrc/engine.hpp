@@ -5,6 +5,7 @@
 #include "plan.hpp"
 #include "spmv.cuh"
 #include "vec.cuh"
+#include "mega.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +38,9 @@ struct Config {
     int graph = 1;
     int unroll = 10;
     int cache = 1;
+    int mega = 1;                // 1: persistent cooperative kernel for the iteration loop where applicable
+    int mega_threads = 0;        // 0 choose (512, else 256)
+    int mega_trace = 0;
     int device = -1;
     int halo_gap = 64;
     int verbose = 0;
@@ -99,6 +103,16 @@ struct SpmvPlan {
     double ms = 0.0;             // measured time of one launch (autotune) or 0
 };
 
+struct MegaPlan {
+    bool ok = false;
+    int threads = 512, stages = 2, cap = 0, grid = 0;
+    size_t smem = 0;
+    int ntiles = 0;
+    int *d_tile_row = nullptr;
+    unsigned *d_tile_nz = nullptr;
+    int *d_cta_tile = nullptr;
+};
+
 } // namespace bicg
 
 // the opaque handle of the C ABI
@@ -113,6 +127,9 @@ struct bicg_matrix {
     unsigned *d_col = nullptr;
     unsigned *d_ptr = nullptr;
     bicg::SpmvPlan plan;
+    bicg::MegaPlan mega;             // persistent-kernel plan (mega.cu)
+    bicg::GridBar *d_bar = nullptr;
+    unsigned long long *d_trace = nullptr;   // BICG_MEGA_TRACE
     // ghost layout
     int ghost_off = 0;           // first ghost column index = roundup(n_loc, 16)
     int n_ghost = 0;

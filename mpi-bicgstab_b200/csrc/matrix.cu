@@ -48,6 +48,9 @@ int set_option(Config &c, const char *key, const char *value)
     else if (k == "GRAPH") c.graph = as_int();
     else if (k == "UNROLL") c.unroll = std::max(1, as_int());
     else if (k == "CACHE") c.cache = as_int();
+    else if (k == "MEGA") c.mega = as_int();
+    else if (k == "MEGA_THREADS") c.mega_threads = as_int();
+    else if (k == "MEGA_TRACE") c.mega_trace = as_int();
     else if (k == "DEVICE") c.device = as_int();
     else if (k == "HALO_GAP") c.halo_gap = std::max(0, as_int());
     else if (k == "VERBOSE") c.verbose = as_int();
@@ -60,7 +63,7 @@ void load_config_from_env(Config &c)
 {
     static const char *keys[] = {"BICG_TOL", "BICG_MAX_ITER", "BICG_OUT_ITER", "BICG_QUIET", "BICG_SPMV",
                                  "BICG_SPMV_LANES", "BICG_SPMV_THREADS", "BICG_SPMV_STAGES", "BICG_SPMV_CTAS",
-                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_DEVICE",
+                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_DEVICE",
                                  "BICG_HALO_GAP", "BICG_VERBOSE", "BICG_FENCE_WRITERS"};
     for (const char *k : keys)
         if (const char *v = getenv(k)) set_option(c, k, v);
@@ -100,6 +103,7 @@ void Context::ensure()
               dev, prop.name, prop.major, prop.minor);
     BICG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int rc = spmv_setup_attributes();
+    if (rc == 0) rc = mega_setup_attributes();
     if (rc != 0) fatal("bicgstab_b200: cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)rc));
     BICG_CUDA(cudaHostAlloc((void **)&h_flags, 64 * 4 * sizeof(int), cudaHostAllocDefault));
     ready = true;
@@ -310,6 +314,57 @@ static void choose_spmv_plan(bicg_matrix *m, const unsigned *h_ptr)
                 m->plan.kind, m->plan.lanes, m->plan.threads, m->plan.stages, m->plan.ctas_per_sm, m->plan.ms);
 }
 
+// Plan of the persistent solver kernel (mega.cu): one CTA per SM, every CTA owns a contiguous, equally sized range
+// of rows, cut into <= threads-row tiles of equal size.
+static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr)
+{
+    Context &c = ctx();
+    MegaPlan &mp = m->mega;
+    mp.ok = false;
+    if (m->n_loc < 1) return;                       // the plan is always built; BICG_MEGA gates its use per solve
+    if (c.cfg.mega != 2 && heuristic_lanes(m->mean_row) != 1) return;   // long rows: sub-warp-per-row kernels (BICG_MEGA=2 forces)
+    const int G = c.sm_count;
+    const long long SMEM_MAX = 224 * 1024;
+    for (int threads : {512, 256}) {
+        if (c.cfg.mega_threads && c.cfg.mega_threads != threads) continue;
+        std::vector<int> tile_row, cta_tile((size_t)G + 1);
+        unsigned max_tile_nnz = 0;
+        for (int g = 0; g < G; ++g) {
+            const long long lo = (long long)m->n_loc * g / G, hi = (long long)m->n_loc * (g + 1) / G;
+            cta_tile[(size_t)g] = (int)tile_row.size();
+            const int len = (int)(hi - lo);
+            const int k = (len + threads - 1) / threads;
+            for (int t = 0; t < k; ++t) {
+                const int r0 = (int)(lo + (long long)len * t / k), r1 = (int)(lo + (long long)len * (t + 1) / k);
+                tile_row.push_back(r0);
+                max_tile_nnz = std::max(max_tile_nnz, h_ptr[r1] - h_ptr[r0]);
+            }
+        }
+        cta_tile[(size_t)G] = (int)tile_row.size();
+        tile_row.push_back(m->n_loc);
+        const int cap = round_up((long long)max_tile_nnz + 8, 32);
+        const long long stage = (long long)cap * 12 + (long long)(threads + 8) * 4;
+        int stages = (int)std::min<long long>(4, SMEM_MAX / stage);
+        if (stages < 2) continue;                       // rows too long for this tile height
+        std::vector<unsigned> tile_nz(tile_row.size());
+        for (size_t i = 0; i < tile_row.size(); ++i) tile_nz[i] = h_ptr[tile_row[i]];
+        mp.threads = threads; mp.stages = stages; mp.cap = cap; mp.grid = G;
+        mp.smem = mega_smem_bytes(cap, stages, threads);
+        mp.ntiles = (int)tile_row.size() - 1;
+        BICG_CUDA(cudaMalloc((void **)&mp.d_tile_row, tile_row.size() * sizeof(int)));
+        BICG_CUDA(cudaMalloc((void **)&mp.d_tile_nz, tile_nz.size() * sizeof(unsigned)));
+        BICG_CUDA(cudaMalloc((void **)&mp.d_cta_tile, cta_tile.size() * sizeof(int)));
+        BICG_CUDA(cudaMemcpy(mp.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice));
+        BICG_CUDA(cudaMemcpy(mp.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        BICG_CUDA(cudaMemcpy(mp.d_cta_tile, cta_tile.data(), cta_tile.size() * sizeof(int), cudaMemcpyHostToDevice));
+        mp.ok = true;
+        if (c.cfg.verbose)
+            fprintf(stderr, "[bicg mega r%d] threads=%d stages=%d cap=%d tiles=%d smem=%zu\n", m->rank, threads, stages, cap,
+                    mp.ntiles, mp.smem);
+        return;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // matrix creation
 // ------------------------------------------------------------------------------------------------
@@ -395,7 +450,8 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     const size_t hist_off = off;  off = align(off + (size_t)m->hist_cap * sizeof(double));
     const size_t mail_off = off;  off = align(off + 2 * MAX_RANKS * sizeof(Mailbox));
     const size_t hflag_off = off; off = align(off + MAX_RANKS * sizeof(HaloFlag));
-    m->arena_bytes = off;
+    const size_t bar_off = off;   off = align(off + sizeof(GridBar));
+    m->arena_bytes = std::max<size_t>(off, (size_t)4 << 20);     // its own allocation granule: the IPC handle maps exactly this
     BICG_CUDA(cudaMalloc((void **)&m->arena, m->arena_bytes));
     BICG_CUDA(cudaMemsetAsync(m->arena, 0, m->arena_bytes, c.stream));
     m->vec_base = (double *)(m->arena + vec_off);
@@ -404,6 +460,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     m->d_hist = (double *)(m->arena + hist_off);
     m->d_mail = (Mailbox *)(m->arena + mail_off);
     m->d_hflag = (HaloFlag *)(m->arena + hflag_off);
+    m->d_bar = (GridBar *)(m->arena + bar_off);
     BICG_CUDA(cudaStreamSynchronize(c.stream));            // arena zeroed before any peer may write into it
 
     lap("arena alloc + zero");
@@ -462,6 +519,11 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
 
     // ---- SpMV plan ------------------------------------------------------------------------------------
     choose_spmv_plan(m, h_ptr);
+    build_mega_plan(m, h_ptr);
+    if (c.cfg.mega_trace) {
+        BICG_CUDA(cudaMalloc((void **)&m->d_trace, (size_t)MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS * sizeof(unsigned long long)));
+        BICG_CUDA(cudaMemset(m->d_trace, 0, (size_t)MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS * sizeof(unsigned long long)));
+    }
 
     lap("spmv plan");
     BICG_CUDA(cudaEventRecord(ev1, c.stream));
@@ -495,6 +557,10 @@ void matrix_destroy(bicg_matrix *m)
     }
     for (int s = 0; s < m->npush; ++s) cudaFree(m->d_push_runs[s]);
     free_plan(m->plan);
+    if (m->d_trace) cudaFree(m->d_trace);
+    if (m->mega.d_tile_row) cudaFree(m->mega.d_tile_row);
+    if (m->mega.d_tile_nz) cudaFree(m->mega.d_tile_nz);
+    if (m->mega.d_cta_tile) cudaFree(m->mega.d_cta_tile);
     if (m->hist_extra) cudaFree(m->hist_extra);
     cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_ptr); cudaFree(m->arena);
     delete m;

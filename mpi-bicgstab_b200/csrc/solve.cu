@@ -60,6 +60,42 @@ struct Seq {
         return v;
     }
 
+    // where the runs of vector `id` that peers need go: their ghost slots, addressed through the IPC mappings
+    PushDesc make_push(int id) const
+    {
+        PushDesc pd{};
+        if (m->world == 1) return pd;
+        pd.npeers = m->npush;
+        pd.fence_writers = c.cfg.fence_writers;
+        pd.src = m->vec(id);
+        for (int s = 0; s < m->npush; ++s) {
+            const int d = m->push_peer[s];
+            pd.dst[s] = (double *)((char *)m->peer_base[d] + m->peer_vec_off[d]) + (long long)id * m->peer_vstride[d] +
+                        m->peer_ghost_off[d];
+            pd.runs[s] = m->d_push_runs[s];
+            pd.nruns[s] = m->push_nruns[s];
+        }
+        return pd;
+    }
+
+    // the persistent kernel runs the whole loop (mega.cu)
+    void mega(int method)
+    {
+        MegaArgs a{};
+        a.sc = m->d_sc; a.partials = m->d_partials; a.hist = m->d_hist; a.comm = m->comm; a.bar = m->d_bar;
+        a.val = m->d_val; a.col = m->d_col; a.ptr = m->d_ptr;
+        a.tile_row = m->mega.d_tile_row; a.tile_nz = m->mega.d_tile_nz; a.cta_tile = m->mega.d_cta_tile;
+        a.cap = m->mega.cap; a.stages = m->mega.stages;
+        a.v = ptrs();
+        a.push_p = make_push(V_P); a.push_r = make_push(V_R); a.push_s = make_push(V_S);
+        a.push_z = make_push(V_Z); a.push_w = make_push(V_W);
+        a.method = method;
+        a.trace = m->d_trace;
+        int rc = launch_mega(m->mega.threads, m->mega.grid, m->mega.smem, a, c.stream);
+        if (rc) fatal("bicgstab_b200: persistent kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        ++launches; ++c.launches;
+    }
+
     // one fused vector kernel; push_vec >= 0: that vector is the next SpMV's input
     void vec(int phase, TailDesc tail, int push_vec = -1)
     {
@@ -70,16 +106,7 @@ struct Seq {
         a.push.npeers = 0; a.push.src = nullptr;
         if (push_vec >= 0 && m->world > 1) {
             a.kc.tail.signal_halo = 1;               // every rank advances its halo epoch, senders also signal
-            a.push.npeers = m->npush;
-            a.push.fence_writers = c.cfg.fence_writers;
-            a.push.src = m->vec(push_vec);
-            for (int s = 0; s < m->npush; ++s) {
-                const int d = m->push_peer[s];
-                a.push.dst[s] = (double *)((char *)m->peer_base[d] + m->peer_vec_off[d]) +
-                                (long long)push_vec * m->peer_vstride[d] + m->peer_ghost_off[d];
-                a.push.runs[s] = m->d_push_runs[s];
-                a.push.nruns[s] = m->push_nruns[s];
-            }
+            a.push = make_push(push_vec);
         } else if (phase == PH_PUSH) {
             return;                                   // single rank: nothing to exchange
         }
@@ -254,7 +281,8 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
         // p, s, z, v, t start at zero: the defined version of the reference's uninitialised reads
         const int zero_ids[5] = {(int)V_P, (int)V_S, (int)V_Z, (int)V_V, (int)V_T};
         for (int id : zero_ids)
-            BICG_CUDA(cudaMemsetAsync(m->vec(id), 0, (size_t)m->vstride * sizeof(double), c.stream));
+            BICG_CUDA(cudaMemsetAsync(m->vec(id), 0, (size_t)m->ghost_off * sizeof(double), c.stream));   // own part only:
+            // the ghost tail belongs to the peers, who may already be pushing into it
     }
     if (method == BICG_METHOD_PIPE_RR)
         BICG_CUDA(cudaMemcpyAsync(m->vec(V_B), m->vec(V_R), vbytes, cudaMemcpyDeviceToDevice, c.stream));   // solver.c:475
@@ -266,14 +294,16 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
     if (method == BICG_METHOD_BICGSTAB) seq.bicgstab_init();
     else seq.capipe_init(method != BICG_METHOD_CA);
 
+    const bool use_mega = cfg.mega && m->mega.ok && !c.prof_on && method != BICG_METHOD_PIPE_RR;
+    if (use_mega) seq.mega(method);
     const bool use_graph = cfg.graph && !c.prof_on && method != BICG_METHOD_PIPE_RR;
     const int U = std::max(1, cfg.unroll);
     const int batches = (max_iter + U - 1) / U;
     const int DEPTH = 3, RING = 64;
     std::vector<cudaEvent_t> ring((size_t)RING, nullptr);
-    if (use_graph) ensure_graph(m, method, U);
+    if (use_graph && !use_mega) ensure_graph(m, method, U);
     int launched_batches = 0;
-    for (int b = 0; b < batches; ++b) {
+    for (int b = 0; b < batches && !use_mega; ++b) {
         if (b >= DEPTH) {
             const int o = (b - DEPTH) % RING;
             BICG_CUDA(cudaEventSynchronize(ring[(size_t)o]));
@@ -314,6 +344,22 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
     (void)launched_batches;
 
     if (hs.error) fatal("bicgstab_b200: rank %d timed out waiting for a peer GPU (halo or reduction mailbox)", m->rank);
+    if (m->d_trace && use_mega && method == BICG_METHOD_BICGSTAB) {
+        // BICG_MEGA_TRACE=1: where CTA 0 of the persistent kernel spent its time, averaged over the iterations
+        const int iters = std::min(hs.k - 1, (int)MEGA_TRACE_ITERS);
+        std::vector<unsigned long long> tr((size_t)MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS);
+        BICG_CUDA(cudaMemcpy(tr.data(), m->d_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        static const char *names[10] = {"spmv s=Ap", "bar alpha", "vec q +push", "bar halo q", "spmv y=Aq", "bar omega",
+                                        "vec x,r", "bar beta", "vec p +push", "bar halo p"};
+        double sum[10] = {0};
+        for (int it = 1; it < iters; ++it)
+            for (int k = 0; k < 10; ++k)
+                sum[k] += (double)(tr[(size_t)it * MEGA_TRACE_SLOTS + k + 1] - tr[(size_t)it * MEGA_TRACE_SLOTS + k]);
+        fprintf(stderr, "[bicg mega trace r%d] us per iteration (CTA 0):", m->rank);
+        double tot = 0;
+        for (int k = 0; k < 10; ++k) { fprintf(stderr, " %s %.1f |", names[k], sum[k] / std::max(1, iters - 1) * 1e-3); tot += sum[k]; }
+        fprintf(stderr, " total %.1f\n", tot / std::max(1, iters - 1) * 1e-3);
+    }
 
     bicg_stats st{};
     st.iters = hs.k;
@@ -346,7 +392,11 @@ int spmv_host(bicg_matrix *m, const double *x_loc, double *y_loc, double *x_full
     reset_state_kernel<<<1, 1, 0, c.stream>>>(m->d_sc, c.cfg.tol, c.cfg.max_iter);
     Seq seq(m);
     seq.vec(PH_PUSH, tail_none(), V_X);
-    seq.spmv(V_X, V_AX, tail_none());
+    // With peers the SpMV ends in an (empty) cross-GPU reduction = a barrier: nobody may push the next x into a
+    // neighbour's ghost slots while that neighbour is still gathering from them.  Inside the solvers the dot
+    // reductions provide this ordering; a bare SpMV (main.c:113) needs it explicitly, like the collective
+    // MPI_Iallgatherv it replaces (matrix.c:432).
+    seq.spmv(V_X, V_AX, m->world > 1 ? tail_allreduce(FIN_NONE, 0) : tail_none());
     BICG_CUDA(cudaMemcpyAsync(y_loc, m->vec(V_AX), vbytes, cudaMemcpyDeviceToHost, c.stream));
     BICG_CUDA(cudaStreamSynchronize(c.stream));
     Scalars hs;

@@ -38,9 +38,9 @@ def main():
         y_ref = O.spmv(n, ptr, col, val, xg, long_double=True)[lo:lo + nloc]
         assert np.abs(y - y_ref).max() <= 1e-13 * np.abs(y_ref).max(), ("spmv", kind, rank)
         b_ref = O.spmv(n, ptr, col, val, np.ones(n), P=world)
-        for method in METHODS:
+        for method, mega in [(m_, g_) for m_ in METHODS for g_ in ((1, 0) if not m_.endswith("rr") else (0,))]:
             kw = RR if method.endswith("rr") else {}
-            B.set_options(tol=TOL, max_iter=600)
+            B.set_options(tol=TOL, max_iter=600, mega=mega)
             b = dm.spmv(np.ones(nloc))
             x = np.zeros(nloc)
             it, st = dm.solve(method, x, b, **kw)
@@ -57,7 +57,7 @@ def main():
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
             assert torch.equal(tmax, tmin), "ranks disagree on iteration count / residual"
             if rank == 0:
-                print(f"[mgpu {world}] {kind:10s} {method:17s} {it:4d} it (oracle {ref['iters']}), launches {st['kernel_launches']}", flush=True)
+                print(f"[mgpu {world}] {kind:10s} {method:17s} mega={mega} {it:4d} it (oracle {ref['iters']}), launches {st['kernel_launches']}", flush=True)
         dm.destroy()
     # the reference-facing host-pointer entry point, collectively
     blk = B.gen_block("stencil15", 14, 14.0, rank=rank, world=world)

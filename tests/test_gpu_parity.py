@@ -18,10 +18,12 @@ TOL = 1e-10
 H_FLOOR = 1e-15
 
 
-@pytest.fixture(autouse=True)
-def _quiet(B):
-    B.set_options(quiet=1, tol=1e-15, max_iter=1000, cache=1)
+@pytest.fixture(autouse=True, params=[1, 0], ids=["mega", "multikernel"])
+def _quiet(B, request):
+    """Every test runs twice: iteration loop in the persistent kernel (mega.cu) and as the kernel-per-phase graph."""
+    B.set_options(quiet=1, tol=1e-15, max_iter=1000, cache=1, mega=request.param)
     yield
+    B.set_options(mega=1)
 
 
 @pytest.mark.parametrize("name,kind,g,p0", SMALL_CASES)
@@ -87,7 +89,7 @@ def test_graph_and_stream_paths_agree(B, method):
     n = blk.n
     out = {}
     for graph in (1, 0):
-        B.set_options(tol=1e-9, max_iter=400, graph=graph)
+        B.set_options(tol=1e-9, max_iter=400, graph=graph, mega=0)
         b = B.spmv_ovlap(blk, np.ones(n))
         x = np.zeros(n)
         it = B.solve(method, blk, x, b)
@@ -158,3 +160,22 @@ def test_full_size_properties(B):
     assert true_res <= 1e-7
     assert np.abs(xs - 1).max() <= 1e-5
     dm.destroy()
+
+
+@pytest.mark.parametrize("method", METHODS[:3])
+def test_persistent_and_multikernel_paths_agree(B, method):
+    """Same phases, different partial-sum grouping: histories agree to rounding, iteration counts to +-2."""
+    blk = B.gen_block("convdiff", 40, 1.5)
+    n = blk.n
+    out = {}
+    for mega in (1, 0):
+        B.set_options(tol=1e-10, max_iter=600, mega=mega)
+        b = B.spmv_ovlap(blk, np.ones(n))
+        x = np.zeros(n)
+        it = B.solve(method, blk, x, b)
+        out[mega] = (it, x.copy(), B.last_history().copy(), B.last_stats()["kernel_launches"])
+    assert abs(out[0][0] - out[1][0]) <= 2
+    m = min(10, out[0][0], out[1][0])
+    assert np.allclose(np.sqrt(out[0][2][1:m + 1]), np.sqrt(out[1][2][1:m + 1]), rtol=1e-10, atol=1e-15)
+    assert np.abs(out[0][1] - out[1][1]).max() < 1e-7
+    assert out[1][3] < 10 < out[0][3]            # one launch for the whole loop vs ~5 per iteration
