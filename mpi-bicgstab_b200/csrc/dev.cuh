@@ -399,7 +399,8 @@ __device__ __forceinline__ void tail_warp(const KernelCommon &kc, double (&tot)[
     if (td.signal_halo) {
         // all CTAs fenced their peer stores before taking a ticket; publish the new epoch to receivers
         const unsigned he = sc->halo_epoch + 1u;
-        __threadfence_system();
+        // no extra fence here: every pushing CTA fenced at system scope before its ticket / barrier arrival, and the
+        // release store below orders this thread's observation of those arrivals before the flag
         if (lane < kc.comm.world && ((kc.comm.send_mask >> lane) & 1u))
             st_release_sys(&kc.comm.hflag[lane][kc.comm.rank].epoch, (unsigned long long)he);
         __syncwarp();

@@ -202,6 +202,7 @@ struct Mega {
         c.nbo = -c.be * c.om;
         int i = row_lo + tid;
         for (; i + 3 * CT < row_hi; i += 4 * CT) body<PH, Strided<4, CT>>(a.v, i, c, dot);
+        for (; i + CT < row_hi; i += 2 * CT) body<PH, Strided<2, CT>>(a.v, i, c, dot);
         for (; i < row_hi; i += CT) body<PH, Strided<1, CT>>(a.v, i, c, dot);
     }
     __device__ void push(const PushDesc &pd)
