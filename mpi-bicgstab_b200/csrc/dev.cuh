@@ -136,6 +136,10 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_flag_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
     unsigned long long v;
@@ -399,10 +403,11 @@ __device__ __forceinline__ void tail_warp(const KernelCommon &kc, double (&tot)[
     if (td.signal_halo) {
         // all CTAs fenced their peer stores before taking a ticket; publish the new epoch to receivers
         const unsigned he = sc->halo_epoch + 1u;
-        // no extra fence here: every pushing CTA fenced at system scope before its ticket / barrier arrival, and the
-        // release store below orders this thread's observation of those arrivals before the flag
+        // no fence here: every CTA that pushed fenced at system scope BEFORE its ticket / barrier arrival, this warp
+        // observed all arrivals (acquire) before getting here, so the halo data is already visible system-wide; a
+        // plain system-scope store of the flag is enough (a release store would cost another NVLink round trip)
         if (lane < kc.comm.world && ((kc.comm.send_mask >> lane) & 1u))
-            st_release_sys(&kc.comm.hflag[lane][kc.comm.rank].epoch, (unsigned long long)he);
+            st_flag_sys(&kc.comm.hflag[lane][kc.comm.rank].epoch, (unsigned long long)he);
         __syncwarp();
         if (wait_halo && !halo_wait_epoch(kc.comm, he) && lane == 0) { sc->error = 1; sc->done = 1; }
         if (lane == 0) sc->halo_epoch = he;

@@ -44,7 +44,8 @@ struct Config {
     int device = -1;
     int halo_gap = 64;
     int verbose = 0;
-    int fence_writers = 1;       // halo push: writer threads fence their own peer stores (belt and braces)
+    int fence_writers = 0;       // 1: every thread that stored to a peer also fences at system scope itself (debug aid;
+                                 // the CTA barrier + one system fence per CTA is sufficient and much cheaper)
 };
 
 struct TuneKey {

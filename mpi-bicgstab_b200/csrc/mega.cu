@@ -88,7 +88,7 @@ struct Mega {
 
     // ---------------------------------------------------------------- grid barrier + master work ----------
     template <int NDOT>
-    __device__ void barrier(double (&dot)[NDOT > 0 ? NDOT : 1], TailDesc td)
+    __device__ void barrier(double (&dot)[NDOT > 0 ? NDOT : 1], TailDesc td, bool pushed = false)
     {
         if (NDOT > 0) cblock_sum<(NDOT > 0 ? NDOT : 1), CT>(dot, scratch);
         cbar(CT);                                     // every consumer's stores happen-before thread 0's fence
@@ -96,9 +96,9 @@ struct Mega {
         if (tid == 0) {
 #pragma unroll
             for (int k = 0; k < NDOT; ++k) __stcg(&a.partials[(size_t)blockIdx.x * MAX_DOTS + k], dot[k]);
-            // release: the CTA barrier above + this fence order every store of the CTA (at system scope when
-            // halo data went to peers) before the arrival
-            if (td.signal_halo) __threadfence_system(); else __threadfence();
+            // release: the CTA barrier above + this fence order every store of the CTA (at system scope when this
+            // CTA's rows went to peers) before the arrival
+            if (pushed) __threadfence_system(); else __threadfence();
             const unsigned prev = atomicAdd(&a.bar->count, 1u);
             s_flags[0] = (prev == gridDim.x - 1);
         }
@@ -205,11 +205,12 @@ struct Mega {
         for (; i + CT < row_hi; i += 2 * CT) body<PH, Strided<2, CT>>(a.v, i, c, dot);
         for (; i < row_hi; i += CT) body<PH, Strided<1, CT>>(a.v, i, c, dot);
     }
-    __device__ void push(const PushDesc &pd)
+    __device__ bool push(const PushDesc &pd)          // true: this CTA stored to a peer
     {
-        if (pd.npeers == 0) return;
+        if (pd.npeers == 0 || !push_touches(pd, row_lo, row_hi)) return false;
         cbar(CT);                                     // the rows being pushed are final
         push_chunk(pd, row_lo, row_hi, tid, CT);
+        return true;
     }
     int trace_it = 0;
     __device__ void mark(int slot)
@@ -240,9 +241,9 @@ struct Mega {
             mark(2);
             if (stop_now()) break;
             vec<PH_BICG_Q>(d0);                                             // q = r - alpha s            :94
-            push(a.push_r);
+            const bool pr = push(a.push_r);
             mark(3);
-            barrier<0>(d0, with_halo(td_none()));
+            barrier<0>(d0, with_halo(td_none()), pr);
             mark(4);
             d4[0] = d4[1] = 0.0;
             spmv<EPI_QY_YY>(a.v.r, a.v.y, d4);                              // y = A q, (q,y), (y,y)      :96-102
@@ -257,9 +258,9 @@ struct Mega {
             mark(8);
             if (stop_now()) break;
             vec<PH_BICG_P>(d0);                                             // p                          :117-119
-            push(a.push_p);
+            const bool pp = push(a.push_p);
             mark(9);
-            barrier<0>(d0, with_halo(td_none()));
+            barrier<0>(d0, with_halo(td_none()), pp);
             mark(10);
             ++trace_it;
         }
@@ -271,8 +272,8 @@ struct Mega {
         if (stop_now()) return;
         while (true) {
             vec<PH_CA_PS>(d0);                                              // p, s                       :217-222
-            push(a.push_s);
-            barrier<0>(d0, with_halo(td_none()));
+            const bool ps = push(a.push_s);
+            barrier<0>(d0, with_halo(td_none()), ps);
             d4[0] = 0.0;
             spmv<EPI_NONE>(a.v.s, a.v.z, d4);                               // z = A s                    :224
             cbar(CT);                                                       // own rows of z written by other warps
@@ -281,8 +282,8 @@ struct Mega {
             barrier<2>(d2, td_red(FIN_OMEGA2, 2));
             d1[0] = 0.0;
             vec<PH_CA_XR>(d1);                                              // x, r, local (r,r)          :233-236
-            push(a.push_r);
-            barrier<1>(d1, with_halo(td_pend(1)));
+            const bool pr = push(a.push_r);
+            barrier<1>(d1, with_halo(td_pend(1)), pr);
             d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
             spmv<EPI_CA4>(a.v.r, a.v.w, d4);                                // w = A r, 4 dots            :238-247
             barrier<4>(d4, td_red(FIN_CAPIPE_END, 4, 1));                   // beta, alpha, k++, test     :248-253
@@ -297,15 +298,15 @@ struct Mega {
         while (true) {
             d2[0] = d2[1] = 0.0;
             vec<PH_PIPE_1>(d2);                                             // p,s,z,q,y + (q,y),(y,y)    :352-364
-            push(a.push_z);
-            barrier<2>(d2, with_halo(td_post(2)));                          // MPI_Iallreduce x2
+            const bool pz = push(a.push_z);
+            barrier<2>(d2, with_halo(td_post(2)), pz);                          // MPI_Iallreduce x2
             d4[0] = 0.0;
             spmv<EPI_NONE>(a.v.z, a.v.v, d4);                               // v = A z                    :365
             barrier<0>(d0, td_complete(FIN_OMEGA2, 2));                     // MPI_Wait x2 -> omega       :366-369
             d5[0] = d5[1] = d5[2] = d5[3] = d5[4] = 0.0;
             vec<PH_PIPE_3>(d5);                                             // x, r, w + 5 dots           :370-380
-            push(a.push_w);
-            barrier<5>(d5, with_halo(td_post(5)));
+            const bool pw = push(a.push_w);
+            barrier<5>(d5, with_halo(td_post(5)), pw);
             spmv<EPI_NONE>(a.v.w, a.v.t, d4);                               // t = A w                    :381
             barrier<0>(d0, td_complete(FIN_CAPIPE_END, 5));                 // MPI_Wait x5 -> beta, alpha :382-388
             if (stop_now()) break;

@@ -78,8 +78,8 @@ struct Seq {
         return pd;
     }
 
-    // the persistent kernel runs the whole loop (mega.cu)
-    void mega(int method)
+    // the persistent kernel runs the whole loop (mega.cu); false: it could not be launched
+    bool mega(int method)
     {
         MegaArgs a{};
         a.sc = m->d_sc; a.partials = m->d_partials; a.hist = m->d_hist; a.comm = m->comm; a.bar = m->d_bar;
@@ -92,8 +92,17 @@ struct Seq {
         a.method = method;
         a.trace = m->d_trace;
         int rc = launch_mega(m->mega.threads, m->mega.grid, m->mega.smem, a, c.stream);
-        if (rc) fatal("bicgstab_b200: persistent kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        if (rc) {
+            // e.g. the grid cannot be co-resident because something else holds SMs: not an error, the
+            // kernel-per-phase path below does the same job
+            (void)cudaGetLastError();
+            if (c.cfg.verbose) fprintf(stderr, "[bicg] persistent kernel not launched (%s); using the per-phase kernels\n",
+                                       cudaGetErrorString((cudaError_t)rc));
+            m->mega.ok = false;
+            return false;
+        }
         ++launches; ++c.launches;
+        return true;
     }
 
     // one fused vector kernel; push_vec >= 0: that vector is the next SpMV's input
@@ -294,8 +303,8 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
     if (method == BICG_METHOD_BICGSTAB) seq.bicgstab_init();
     else seq.capipe_init(method != BICG_METHOD_CA);
 
-    const bool use_mega = cfg.mega && m->mega.ok && !c.prof_on && method != BICG_METHOD_PIPE_RR;
-    if (use_mega) seq.mega(method);
+    bool use_mega = cfg.mega && m->mega.ok && !c.prof_on && method != BICG_METHOD_PIPE_RR;
+    if (use_mega) use_mega = seq.mega(method);
     const bool use_graph = cfg.graph && !c.prof_on && method != BICG_METHOD_PIPE_RR;
     const int U = std::max(1, cfg.unroll);
     const int batches = (max_iter + U - 1) / U;

@@ -201,7 +201,7 @@ __device__ __forceinline__ void body(const VecPtrs &v, int i, const Coef &c, dou
 
 
 // copy the parts of this CTA's chunk [lo, hi) that peers need into their ghost regions (peer stores)
-__device__ __forceinline__ void push_chunk(const PushDesc &pd, int lo, int hi, int tid, int nthreads)
+__device__ __forceinline__ bool push_chunk(const PushDesc &pd, int lo, int hi, int tid, int nthreads)
 {
     bool stored = false;
     for (int pi = 0; pi < pd.npeers; ++pi) {
@@ -234,7 +234,23 @@ __device__ __forceinline__ void push_chunk(const PushDesc &pd, int lo, int hi, i
     // a thread that wrote to a peer orders its own NVLink stores before anything that follows (the halo flag
     // is released by the tail after a CTA barrier, a grid-wide ticket and another system fence)
     if (stored && pd.fence_writers) __threadfence_system();
+    return stored;
 }
 
+
+// does the row range [lo, hi) contain anything a peer needs?  (decides which CTAs pay for a system-scope fence)
+__device__ __forceinline__ bool push_touches(const PushDesc &pd, int lo, int hi)
+{
+    for (int pi = 0; pi < pd.npeers; ++pi) {
+        const PushRun *runs = pd.runs[pi];
+        int a = 0, b = pd.nruns[pi];
+        while (a < b) {
+            const int m = (a + b) >> 1;
+            if (runs[m].src + runs[m].len <= lo) a = m + 1; else b = m;
+        }
+        if (a < pd.nruns[pi] && runs[a].src < hi) return true;
+    }
+    return false;
+}
 
 } // namespace bicg
