@@ -229,7 +229,7 @@ def run_b200(args, w):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG"] = "WARN"            # NCCL's version banner goes to stdout; stdout carries ONE JSON line
+    os.environ.pop("NCCL_DEBUG", None)           # NCCL's version banner goes to stdout; stdout carries ONE JSON line
     torch.cuda.set_device(local)
     B.set_options(device=local, quiet=1)
     if world > 1:

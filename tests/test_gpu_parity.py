@@ -179,3 +179,42 @@ def test_persistent_and_multikernel_paths_agree(B, method):
     assert np.allclose(np.sqrt(out[0][2][1:m + 1]), np.sqrt(out[1][2][1:m + 1]), rtol=1e-10, atol=1e-15)
     assert np.abs(out[0][1] - out[1][1]).max() < 1e-7
     assert out[1][3] < 10 < out[0][3]            # one launch for the whole loop vs ~5 per iteration
+
+
+def _write_mtx(path, blk, B):
+    import scipy.sparse as sp
+    ptr, col, val = B.block_to_global_csr(blk)
+    A = sp.csr_matrix((val, col, ptr), shape=(blk.n, blk.n)).tocsc().tocoo()
+    with open(path, "w") as fh:
+        fh.write("%%MatrixMarket matrix coordinate real general\n")
+        fh.write(f"{blk.n} {blk.n} {A.nnz}\n")
+        for r, c, v in zip(A.row, A.col, A.data):
+            fh.write(f"{r + 1} {c + 1} {float(v)!r}\n")
+    return ptr, col, val
+
+
+def test_reference_main_c_runs_on_the_library(B, O, tmp_path):
+    """The drop-in itself: the reference's UNCHANGED main.c (built in the dev container into oracle/_ref/ref_main_b200,
+    linked against libbicgstab_b200.so) loads a Matrix-Market file, forms b = A*1 and solves on the GPU; its stdout
+    is the reference's (main.c:52, 93; solver.c:124, 135-139) and its iteration count the oracle's."""
+    import os, re, subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_main_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_main_b200 not built (needs /root/reference at build time)")
+    blk = B.gen_block("convdiff", 36, 1.5)
+    f = tmp_path / "cd36.mtx"
+    ptr, col, val = _write_mtx(f, blk, B)
+    n = blk.n
+    b = O.spmv(n, ptr, col, val, np.ones(n))
+    for method, extra in (("bicgstab", []), ("ca_bicgstab", []), ("pipe_bicgstab_rr", ["10", "3"])):
+        kw = dict(krr=10, nrr=3) if extra else {}
+        env = dict(os.environ, BICG_TOL="1e-10", BICG_MAX_ITER="600", BICG_OUT_ITER="10")
+        p = subprocess.run([exe, str(f), method] + extra, capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        out = p.stdout
+        assert out.startswith("Node: 1, Proc: 1\n") and "IO time      : " in out
+        it = int(re.search(r"Total iter\s*:\s*(\d+)", out).group(1))
+        ref = O.solve(method, n, ptr, col, val, b, tol=1e-10, max_iter=600, **kw)
+        assert abs(it - ref["iters"]) <= 2, (method, it, ref["iters"])
+        assert re.search(r"Iteration: 10, Residual: \d\.\d{6}e[-+]\d\d", out)
+        assert float(re.search(r"Final r\s*:\s*(\S+)", out).group(1)) <= 1e-10
