@@ -328,6 +328,7 @@ def run_b200(args, w):
                        "converged": bool(converged), "final_relative_residual": final_res,
                        "l2": "inputs larger than L2 (matrix stream %.0f MB per SpMV > 126 MB L2)" % (12e-6 * blk.nnz_loc),
                        "spmv_plan": {"kind": ["tma", "rowsplit"][st.spmv_kind], "lanes": st.spmv_lanes},
+                       "spmv_effective_GBps_all_gpus": world * (12.0 * blk.nnz_loc + 20.0 * n_loc + 4) / (k_ms * 1e-3) / 1e9,
                        "algorithmic_bytes_per_iteration": bytes_iter,
                        "solver_effective_GBps": bytes_iter * iters / (ms * 1e-3) / 1e9},
             "clocks": clocks,

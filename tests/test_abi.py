@@ -156,3 +156,30 @@ def test_reference_main_c_links_against_the_library(B, tmp_path):
     for sym in ("bicgstab", "ca_bicgstab", "pipe_bicgstab", "pipe_bicgstab_rr", "MPI_csr_spmv_ovlap",
                 "MPI_csr_load_matrix_block", "csr_init_matrix", "csr_free_matrix"):
         assert re.search(r"\bU %s\b" % sym, undefined), sym
+
+
+def test_halo_runs_gap_merging(B):
+    """plan_halo_runs: gap = 0 gives exactly the referenced columns, a larger gap merges runs and never loses one."""
+    blk = B.gen_block("random", 4000, 6, rank=1, world=4)
+    cols = np.unique(np.asarray(blk.offd_arrays()[1])[:int(blk.offd.nz)]).astype(np.int64)
+    for gap in (0, 3, 64, 10**6):
+        out = (C.c_int * (3 * (cols.size + 1)))()
+        k = B.lib.bicg_plan_halo_runs(C.byref(blk.offd), C.byref(blk.info), 1, 4, gap, out, len(out))
+        runs = np.array(out[:3 * k]).reshape(-1, 3)
+        covered = np.concatenate([np.arange(f, f + l) for f, l, _ in runs]) if k else np.zeros(0, dtype=np.int64)
+        assert np.all(np.diff(runs[:, 0]) > 0) and set(cols) <= set(covered)
+        lo, cnt = blk.displs, blk.recvcounts
+        for f, l, o in runs:                       # a run never leaves its owner's row range, never touches rank 1
+            assert o != 1 and lo[o] <= f and f + l <= lo[o] + cnt[o]
+        if gap == 0:
+            assert covered.size == cols.size
+        if gap == 10**6:
+            assert k <= 3                          # one run per owner
+
+
+def test_options_and_unknown_keys(B):
+    B.set_options(tol=1e-9, max_iter=77, out_iter=5, unroll=4, graph=0, cache=1, mega=1)
+    with pytest.raises(KeyError):
+        B.set_option("NO_SUCH_OPTION", 1)
+    B.set_options(tol=1e-15, max_iter=1000, out_iter=100, unroll=10, graph=1)
+    assert B.lib.bicg_comm_rank() == 0 and B.lib.bicg_comm_world() == 1 and B.lib.bicg_comm_selftest() == 0
