@@ -220,6 +220,28 @@ def run_reference(args, w):
     print(json.dumps(line))
 
 
+def bind_near_gpu(index):
+    """Pin this process to the cores of the GPU's NUMA node (what `numactl --cpunodebind` would do), so that the
+    pinned host buffers of the e2e leg are allocated next to the GPU's PCIe root.  Returns the previous affinity."""
+    prev = os.sched_getaffinity(0)
+    try:
+        bdf = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]                                     # sysfs uses a 4-digit PCI domain
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        near = prev & cpus
+        if near:
+            os.sched_setaffinity(0, near)
+    except Exception:
+        pass
+    return prev
+
+
 # ---------------------------------------------------------------------------------------------------------
 def run_b200(args, w):
     import torch
@@ -230,6 +252,7 @@ def run_b200(args, w):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.pop("NCCL_DEBUG", None)           # NCCL's version banner goes to stdout; stdout carries ONE JSON line
+    full_affinity = bind_near_gpu(local)
     torch.cuda.set_device(local)
     B.set_options(device=local, quiet=1)
     if world > 1:
@@ -346,6 +369,7 @@ def run_b200(args, w):
         }
         if world == 1 and not args.no_cpu:
             try:
+                os.sched_setaffinity(0, full_affinity)      # the CPU reference may use every core of the box
                 r = reference_sample(w, REF_ITERS)
                 if r:
                     line["cpu_baseline"] = {"value": 1.0 / r["avg_time_per_iter_s"], "unit": "iterations/s",

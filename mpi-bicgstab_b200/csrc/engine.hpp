@@ -85,6 +85,14 @@ struct Context {
     int launches = 0;
 
     void ensure();               // lazy device init; fails loudly if there is no usable GPU
+    // device-memory cache: cudaMalloc / cudaFree are synchronising driver calls that cost milliseconds for the
+    // 100 MB-class buffers of a matrix; blocks are kept by exact size and reused by the next upload
+    void *dev_alloc(size_t bytes);
+    void  dev_free(void *p);
+    void  dev_release_all();
+    std::multimap<size_t, void *> pool;
+    std::map<void *, size_t> live;
+    size_t pool_bytes = 0;
     void host_allgather(const void *send, void *recv, size_t bytes);
 };
 Context &ctx();

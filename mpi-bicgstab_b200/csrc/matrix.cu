@@ -109,6 +109,48 @@ void Context::ensure()
     ready = true;
 }
 
+void *Context::dev_alloc(size_t bytes)
+{
+    bytes = (bytes + 511) & ~(size_t)511;
+    void *p = nullptr;
+    auto it = pool.find(bytes);
+    if (it != pool.end()) {
+        p = it->second;
+        pool.erase(it);
+        pool_bytes -= bytes;
+    } else {
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess && pool_bytes) {          // give the cached blocks back and retry once
+            (void)cudaGetLastError();
+            dev_release_all();
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess) fatal("bicgstab_b200: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    live[p] = bytes;
+    return p;
+}
+
+void Context::dev_free(void *p)
+{
+    if (!p) return;
+    auto it = live.find(p);
+    if (it == live.end()) { cudaFree(p); return; }
+    const size_t bytes = it->second;
+    live.erase(it);
+    const size_t LIMIT = (size_t)16 << 30;             // keep at most 16 GB parked
+    if (pool_bytes + bytes > LIMIT) { cudaFree(p); return; }
+    pool.emplace(bytes, p);
+    pool_bytes += bytes;
+}
+
+void Context::dev_release_all()
+{
+    for (auto &kv : pool) cudaFree(kv.second);
+    pool.clear();
+    pool_bytes = 0;
+}
+
 void Context::host_allgather(const void *send, void *recv, size_t bytes)
 {
     if (world == 1) { memcpy(recv, send, bytes); return; }
@@ -123,8 +165,8 @@ static inline int round_up(long long v, int m) { return (int)(((v + m - 1) / m) 
 
 static void free_plan(SpmvPlan &p)
 {
-    if (p.d_tile_row) cudaFree(p.d_tile_row);
-    if (p.d_tile_nz) cudaFree(p.d_tile_nz);
+    ctx().dev_free(p.d_tile_row);
+    ctx().dev_free(p.d_tile_nz);
     p.d_tile_row = nullptr; p.d_tile_nz = nullptr;
 }
 
@@ -161,8 +203,8 @@ static bool build_tma_plan(const bicg_matrix *m, const unsigned *h_ptr, int lane
     out.ctas_per_sm = std::max(1, std::min({by_smem, 2048 / (threads + 32), want_ctas > 0 ? want_ctas : 8}));
     out.ntiles = nt;
     out.grid = std::max(1, std::min(nt, c.sm_count * out.ctas_per_sm));
-    BICG_CUDA(cudaMalloc((void **)&out.d_tile_row, tile_row.size() * sizeof(int)));
-    BICG_CUDA(cudaMalloc((void **)&out.d_tile_nz, tile_nz.size() * sizeof(unsigned)));
+    out.d_tile_row = (decltype(out.d_tile_row))c.dev_alloc(tile_row.size() * sizeof(int));
+    out.d_tile_nz = (decltype(out.d_tile_nz))c.dev_alloc(tile_nz.size() * sizeof(unsigned));
     BICG_CUDA(cudaMemcpyAsync(out.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     BICG_CUDA(cudaMemcpyAsync(out.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
     BICG_CUDA(cudaStreamSynchronize(c.stream));   // the host vectors die here
@@ -351,9 +393,9 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr)
         mp.threads = threads; mp.stages = stages; mp.cap = cap; mp.grid = G;
         mp.smem = mega_smem_bytes(cap, stages, threads);
         mp.ntiles = (int)tile_row.size() - 1;
-        BICG_CUDA(cudaMalloc((void **)&mp.d_tile_row, tile_row.size() * sizeof(int)));
-        BICG_CUDA(cudaMalloc((void **)&mp.d_tile_nz, tile_nz.size() * sizeof(unsigned)));
-        BICG_CUDA(cudaMalloc((void **)&mp.d_cta_tile, cta_tile.size() * sizeof(int)));
+        mp.d_tile_row = (decltype(mp.d_tile_row))c.dev_alloc(tile_row.size() * sizeof(int));
+        mp.d_tile_nz = (decltype(mp.d_tile_nz))c.dev_alloc(tile_nz.size() * sizeof(unsigned));
+        mp.d_cta_tile = (decltype(mp.d_cta_tile))c.dev_alloc(cta_tile.size() * sizeof(int));
         BICG_CUDA(cudaMemcpy(mp.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice));
         BICG_CUDA(cudaMemcpy(mp.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
         BICG_CUDA(cudaMemcpy(mp.d_cta_tile, cta_tile.data(), cta_tile.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -426,9 +468,9 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     m->mean_row = m->n_loc ? (double)m->nnz / m->n_loc : 0.0;
 
     const size_t pad = 16;
-    BICG_CUDA(cudaMalloc((void **)&m->d_val, (m->nnz + pad) * sizeof(double)));
-    BICG_CUDA(cudaMalloc((void **)&m->d_col, (m->nnz + pad) * sizeof(unsigned)));
-    BICG_CUDA(cudaMalloc((void **)&m->d_ptr, ((size_t)m->n_loc + 1 + pad) * sizeof(unsigned)));
+    m->d_val = (decltype(m->d_val))c.dev_alloc((m->nnz + pad) * sizeof(double));
+    m->d_col = (decltype(m->d_col))c.dev_alloc((m->nnz + pad) * sizeof(unsigned));
+    m->d_ptr = (decltype(m->d_ptr))c.dev_alloc(((size_t)m->n_loc + 1 + pad) * sizeof(unsigned));
     BICG_CUDA(cudaMemsetAsync(m->d_ptr + m->n_loc + 1, 0, pad * sizeof(unsigned), c.stream));
     BICG_CUDA(cudaMemsetAsync(m->d_val + m->nnz, 0, pad * sizeof(double), c.stream));
     BICG_CUDA(cudaMemsetAsync(m->d_col + m->nnz, 0, pad * sizeof(unsigned), c.stream));
@@ -452,7 +494,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     const size_t hflag_off = off; off = align(off + MAX_RANKS * sizeof(HaloFlag));
     const size_t bar_off = off;   off = align(off + sizeof(GridBar));
     m->arena_bytes = std::max<size_t>(off, (size_t)4 << 20);     // its own allocation granule: the IPC handle maps exactly this
-    BICG_CUDA(cudaMalloc((void **)&m->arena, m->arena_bytes));
+    m->arena = (decltype(m->arena))c.dev_alloc(m->arena_bytes);
     BICG_CUDA(cudaMemsetAsync(m->arena, 0, m->arena_bytes, c.stream));
     m->vec_base = (double *)(m->arena + vec_off);
     m->d_sc = (Scalars *)(m->arena + sc_off);
@@ -505,7 +547,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
             send_mask |= 1u << p;
             const int slot = m->npush++;
             m->push_peer[slot] = p; m->push_nruns[slot] = (int)pr.size();
-            BICG_CUDA(cudaMalloc((void **)&m->d_push_runs[slot], pr.size() * sizeof(PushRun)));
+            m->d_push_runs[slot] = (PushRun *)c.dev_alloc(pr.size() * sizeof(PushRun));
             BICG_CUDA(cudaMemcpy(m->d_push_runs[slot], pr.data(), pr.size() * sizeof(PushRun), cudaMemcpyHostToDevice));
         }
         m->comm.recv_mask = recv_mask; m->comm.send_mask = send_mask;
@@ -521,7 +563,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     choose_spmv_plan(m, h_ptr);
     build_mega_plan(m, h_ptr);
     if (c.cfg.mega_trace) {
-        BICG_CUDA(cudaMalloc((void **)&m->d_trace, (size_t)MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS * sizeof(unsigned long long)));
+        m->d_trace = (decltype(m->d_trace))c.dev_alloc((size_t)MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS * sizeof(unsigned long long));
         BICG_CUDA(cudaMemset(m->d_trace, 0, (size_t)MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS * sizeof(unsigned long long)));
     }
 
@@ -555,14 +597,12 @@ void matrix_destroy(bicg_matrix *m)
             if (p != m->rank && m->peer_base[p]) cudaIpcCloseMemHandle(m->peer_base[p]);
         c.host_allgather(&token, all.data(), sizeof(int));
     }
-    for (int s = 0; s < m->npush; ++s) cudaFree(m->d_push_runs[s]);
+    for (int s = 0; s < m->npush; ++s) c.dev_free(m->d_push_runs[s]);
     free_plan(m->plan);
-    if (m->d_trace) cudaFree(m->d_trace);
-    if (m->mega.d_tile_row) cudaFree(m->mega.d_tile_row);
-    if (m->mega.d_tile_nz) cudaFree(m->mega.d_tile_nz);
-    if (m->mega.d_cta_tile) cudaFree(m->mega.d_cta_tile);
+    c.dev_free(m->d_trace);
+    c.dev_free(m->mega.d_tile_row); c.dev_free(m->mega.d_tile_nz); c.dev_free(m->mega.d_cta_tile);
     if (m->hist_extra) cudaFree(m->hist_extra);
-    cudaFree(m->d_val); cudaFree(m->d_col); cudaFree(m->d_ptr); cudaFree(m->arena);
+    c.dev_free(m->d_val); c.dev_free(m->d_col); c.dev_free(m->d_ptr); c.dev_free(m->arena);
     delete m;
 }
 
