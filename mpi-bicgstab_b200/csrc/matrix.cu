@@ -494,7 +494,12 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     const size_t hflag_off = off; off = align(off + MAX_RANKS * sizeof(HaloFlag));
     const size_t bar_off = off;   off = align(off + sizeof(GridBar));
     m->arena_bytes = std::max<size_t>(off, (size_t)4 << 20);     // its own allocation granule: the IPC handle maps exactly this
-    m->arena = (decltype(m->arena))c.dev_alloc(m->arena_bytes);
+    if (m->world > 1) {
+        // exported through CUDA IPC: always a fresh allocation of its own (peers map and unmap exactly this one)
+        BICG_CUDA(cudaMalloc((void **)&m->arena, m->arena_bytes));
+    } else {
+        m->arena = (char *)c.dev_alloc(m->arena_bytes);
+    }
     BICG_CUDA(cudaMemsetAsync(m->arena, 0, m->arena_bytes, c.stream));
     m->vec_base = (double *)(m->arena + vec_off);
     m->d_sc = (Scalars *)(m->arena + sc_off);
