@@ -1,0 +1,117 @@
+"""GPU edge cases (-m gpu): ragged and empty rows, rows longer than a shared-memory stage (row-split fallback),
+systems smaller than a warp / than the grid, breakdown (0/0) behaviour -- each against the oracle, on both loop
+implementations (persistent kernel and kernel-per-phase graph)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import METHODS, RR, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=[1, 0], ids=["mega", "multikernel"])
+def _opts(B, request):
+    B.set_options(quiet=1, tol=1e-10, max_iter=500, cache=1, mega=request.param, spmv="auto", spmv_lanes=0)
+    yield
+    B.set_options(mega=1, spmv="auto", spmv_lanes=0, tol=1e-15, max_iter=1000)
+
+
+def _block(B, A):
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    n = A.shape[0]
+    return B.blocks_from_csr(n, A.indptr, A.indices, A.data), n, A.indptr, A.indices, A.data
+
+
+def _ragged(n, seed, max_len, dominant=True):
+    rng = np.random.default_rng(seed)
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        k = int(rng.integers(0, max_len + 1))
+        if k:
+            c = rng.choice(n, size=min(k, n), replace=False)
+            c = c[c != i]
+            rows += [i] * c.size; cols += list(c); vals += list(-rng.random(c.size))
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    if dominant:
+        A = A + sp.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)
+    return A
+
+
+def test_spmv_with_empty_and_ragged_rows(B, O):
+    """Rows of length 0 .. 40 (no diagonal added, so many rows are empty): tiles whose nnz window is empty,
+    threads whose row has nothing to gather."""
+    blk, n, ptr, col, val = _block(B, _ragged(5003, 1, 40, dominant=False))
+    assert np.any(np.diff(ptr) == 0)
+    x = np.random.default_rng(2).standard_normal(n)
+    y = B.spmv_ovlap(blk, x)
+    assert rel_err(y, O.spmv(n, ptr, col, val, x, long_double=True)) <= 1e-13
+    assert np.all(y[np.diff(ptr) == 0] == 0.0)
+
+
+def test_all_rows_empty(B):
+    blk, n, *_ = _block(B, sp.csr_matrix((257, 257)))
+    assert np.all(B.spmv_ovlap(blk, np.ones(n)) == 0.0)
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_ragged_solve(B, O, method):
+    blk, n, ptr, col, val = _block(B, _ragged(4001, 3, 30))
+    kw = RR if method.endswith("rr") else {}
+    b = B.spmv_ovlap(blk, np.ones(n))
+    x = np.zeros(n)
+    it = B.solve(method, blk, x, b, **kw)
+    ref = O.solve(method, n, ptr, col, val, O.spmv(n, ptr, col, val, np.ones(n)), tol=1e-10, max_iter=500, **kw)
+    assert abs(it - ref["iters"]) <= 2 and np.abs(x - 1).max() < 1e-7
+
+
+def test_row_longer_than_a_stage_falls_back_to_rowsplit(B, O):
+    """One dense row of 12 000 entries cannot be staged in shared memory: the plan must pick the row-split kernel
+    (and the persistent kernel must stand aside), results unchanged."""
+    n = 12000
+    A = sp.lil_matrix(_ragged(n, 5, 6))
+    A[7, :] = -1e-3
+    A[7, 7] = 20.0
+    blk, n, ptr, col, val = _block(B, A)
+    x = np.random.default_rng(4).standard_normal(n)
+    assert rel_err(B.spmv_ovlap(blk, x), O.spmv(n, ptr, col, val, x, long_double=True)) <= 1e-13
+    b = B.spmv_ovlap(blk, np.ones(n))
+    xs = np.zeros(n)
+    it = B.bicgstab(blk, xs, b)
+    assert B.last_stats()["spmv_kind"] == 1                  # rowsplit
+    ref = O.solve("bicgstab", n, ptr, col, val, O.spmv(n, ptr, col, val, np.ones(n)), tol=1e-10, max_iter=500)
+    assert abs(it - ref["iters"]) <= 2 and np.abs(xs - 1).max() < 1e-7
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 33, 149])
+@pytest.mark.parametrize("method", METHODS[:3])
+def test_tiny_systems(B, O, n, method):
+    """Fewer rows than a warp, than a tile, than there are CTAs in the persistent kernel."""
+    rng = np.random.default_rng(n)
+    A = sp.csr_matrix(rng.random((n, n)) * (rng.random((n, n)) < 0.6)) + sp.diags(np.full(n, float(n) + 1.0))
+    blk, n, ptr, col, val = _block(B, A)
+    b = B.spmv_ovlap(blk, np.ones(n))
+    x = np.zeros(n)
+    it = B.solve(method, blk, x, b)
+    ref = O.solve(method, n, ptr, col, val, O.spmv(n, ptr, col, val, np.ones(n)), tol=1e-10, max_iter=500)
+    assert abs(it - ref["iters"]) <= 2, (it, ref["iters"])
+    if np.isnan(ref["x"]).any():
+        # n = 1: the first half-step is already exact, q = 0 and omega = 0/0 -- the reference breaks down to NaN
+        # (no breakdown handling) and so must we, at the same iteration
+        assert it == ref["iters"] and np.array_equal(np.isnan(x), np.isnan(ref["x"]))
+    else:
+        assert np.abs(x - 1).max() < 1e-8
+
+
+def test_breakdown_matches_reference_semantics(B, O):
+    """A = I: after one step q = 0, omega = 0/0.  The reference has no breakdown handling: the NaN makes the
+    loop test false and it returns after 1 iteration with NaN in x; so do we."""
+    n = 64
+    blk, n, ptr, col, val = _block(B, sp.identity(n, format="csr"))
+    b = np.ones(n)
+    x = np.zeros(n)
+    it = B.bicgstab(blk, x, b)
+    ref = O.solve("bicgstab", n, ptr, col, val, np.ones(n), tol=1e-10, max_iter=500)
+    assert it == ref["iters"] == 1
+    assert np.array_equal(np.isnan(x), np.isnan(ref["x"]))
