@@ -285,7 +285,7 @@ def run_b200(args, w):
             x_dev.zero_(); r_dev.copy_(b_dev)
             it = B.lib.bicg_solve(dm.h, B.METHODS[method], C.c_void_p(x_dev.data_ptr()), C.c_void_p(r_dev.data_ptr()),
                                   0, 0, 1, C.byref(st))
-            return it, st.kernel_launches
+            return it, st.kernel_launches, st.loop_ms
 
         sampler = ClockSampler(local)
         if rank == 0:
@@ -295,10 +295,10 @@ def run_b200(args, w):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        iters, launches = 0, 0
+        iters, launches, loop_ms = 0, 0, 0.0
         for _ in range(args.steps):
-            it, nl = resident_step()
-            iters += it; launches += nl
+            it, nl, lm = resident_step()
+            iters += it; launches += nl; loop_ms += lm
         e1.record(stream)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
@@ -342,6 +342,33 @@ def run_b200(args, w):
     if rank == 0:
         nnz_glob = int(blk.info.nz) if w["kind"] != "random" else n * int(w["p0"])
         bytes_iter = 24 * nnz_glob + BYTES_PER_ITER_N[method] * n
+        persistent = launches <= 8 * args.steps                   # the loop ran as ONE persistent kernel per solve
+        spmv_obj = {"kernel": "spmv_ws_kernel + fused (r#,s) dot" if st.spmv_kind == 0 else "spmv_rowsplit_kernel + dot",
+                    "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "frac": k_bytes / (k_ms * 1e-3) / 1e9 / peak, "unit": "GB/s",
+                    "algorithmic_bytes_per_launch": k_bytes, "avg_launch_us": k_ms * 1e3,
+                    "traffic": read_traffic("dram_bytes_per_launch"),
+                    "in_per_phase_kernels": {"spmv_avg_us": 1e3 * prof_ms[0] / max(prof_cnt[0], 1),
+                                             "vector_avg_us": 1e3 * prof_ms[1] / max(prof_cnt[1], 1),
+                                             "spmv_share_of_step": prof_ms[0] / max(sum(prof_ms), 1e-12)}}
+        if persistent:
+            # dominant kernel of the timed region = bicg_mega_kernel (one launch per solve): its algorithmic bytes are the
+            # iterations it ran x the per-iteration bytes of SURVEY.md 8(d), per rank; its duration is the library's
+            # CUDA-event time of the reference's timed region (init SpMV + the persistent kernel)
+            per_rank = bytes_iter / world
+            ach = per_rank * iters / (loop_ms * 1e-3) / 1e9
+            tpi = read_traffic("mega_dram_bytes_per_iteration")
+            roofline = {"bound": "hbm", "kernel": f"bicg_mega_kernel (persistent solver loop of {method}: 2 SpMV phases + the fused "
+                                                  "vector phases + 4-5 grid barriers per iteration)",
+                        "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": per_rank * iters / args.steps,
+                        "avg_launch_us": 1e3 * loop_ms / args.steps,
+                        "traffic": (tpi * iters / args.steps) if (tpi and world == 1 and args.workload == "transport"
+                                                                   and method == "bicgstab") else None,
+                        "traffic_note": "ncu dram bytes per iteration of the same kernel on the same matrix x iterations per launch",
+                        "spmv_kernel": spmv_obj}
+        else:
+            roofline = dict(spmv_obj, bound="hbm", peak=peak, peak_source=peak_src)
         line = {
             "metric": "BiCGStab iterations/sec", "value": iters / (ms * 1e-3), "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -358,14 +385,7 @@ def run_b200(args, w):
             "e2e": {"value": e2e_iters / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "spmv_tma_kernel + fused (r#,s) dot" if st.spmv_kind == 0 else "spmv_rowsplit_kernel + dot",
-                         "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": k_bytes / (k_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": k_bytes, "avg_launch_us": k_ms * 1e3,
-                         "traffic": read_traffic(),
-                         "in_solve": {"spmv_avg_us": 1e3 * prof_ms[0] / max(prof_cnt[0], 1),
-                                      "vector_avg_us": 1e3 * prof_ms[1] / max(prof_cnt[1], 1),
-                                      "spmv_share_of_step": prof_ms[0] / max(sum(prof_ms), 1e-12)}},
+            "roofline": roofline,
         }
         if world == 1 and not args.no_cpu:
             try:
@@ -386,11 +406,11 @@ def run_b200(args, w):
         dist.destroy_process_group()
 
 
-def read_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), else None."""
+def read_traffic(key):
+    """dram bytes measured by ncu (committed under profiles/spmv_traffic.json), else None."""
     try:
         with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            return json.load(f).get(key)
     except Exception:
         return None
 
