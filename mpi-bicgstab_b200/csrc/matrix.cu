@@ -51,6 +51,7 @@ int set_option(Config &c, const char *key, const char *value)
     else if (k == "MEGA") c.mega = as_int();
     else if (k == "MEGA_THREADS") c.mega_threads = as_int();
     else if (k == "MEGA_TRACE") c.mega_trace = as_int();
+    else if (k == "MEGA_FUSEQ") c.mega_fuseq = as_int();
     else if (k == "DEVICE") c.device = as_int();
     else if (k == "HALO_GAP") c.halo_gap = std::max(0, as_int());
     else if (k == "VERBOSE") c.verbose = as_int();
@@ -63,7 +64,7 @@ void load_config_from_env(Config &c)
 {
     static const char *keys[] = {"BICG_TOL", "BICG_MAX_ITER", "BICG_OUT_ITER", "BICG_QUIET", "BICG_SPMV",
                                  "BICG_SPMV_LANES", "BICG_SPMV_THREADS", "BICG_SPMV_STAGES", "BICG_SPMV_CTAS",
-                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_DEVICE",
+                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_MEGA_FUSEQ", "BICG_DEVICE",
                                  "BICG_HALO_GAP", "BICG_VERBOSE", "BICG_FENCE_WRITERS"};
     for (const char *k : keys)
         if (const char *v = getenv(k)) set_option(c, k, v);

@@ -265,6 +265,83 @@ struct Mega {
             ++trace_it;
         }
     }
+    // EXPERIMENTAL (BICG_MEGA_FUSEQ=1, off by default, not yet validated on hardware): y = A q with
+    // q[col] = r[col] - alpha s[col] gathered on the fly (solver.c:94 folded into :96), q[row] written to the spare
+    // vector ax, dots (q,y), (y,y).  Removes the q vector phase and one grid barrier per iteration.
+    __device__ void spmv_fq(double alpha, double (&dot)[4])
+    {
+        constexpr int UQ = 8;
+        const int stages = a.stages, cap = a.cap;
+        const double *rv = a.v.r, *sv = a.v.s;
+        for (int lt = 0; lt < my_tiles; ++lt, ++vis) {
+            const int s = (int)(vis % (unsigned)stages);
+            mbar_wait(smem_u32(&full_bar[s]), (vis / (unsigned)stages) & 1u);
+            const unsigned char *st = dyn + (size_t)s * stage_bytes;
+            const double   *sval = reinterpret_cast<const double *>(st);
+            const unsigned *scol = reinterpret_cast<const unsigned *>(sval + cap);
+            const unsigned *sptr = scol + cap;
+            const StageHdr h = hdr[s];
+            const int row = h.row0 + tid;
+            const bool valid = row < h.row1;
+            int j = 0, e = 0;
+            double r_row = 0.0, s_row = 0.0;
+            if (valid) {
+                j = (int)(sptr[row - h.rowa] - h.a0);
+                e = (int)(sptr[row - h.rowa + 1] - h.a0);
+                r_row = rv[row]; s_row = sv[row];
+            }
+            double acc = 0.0;
+            while (j < e) {
+                unsigned c[UQ];
+                double v[UQ], xr[UQ], xs[UQ];
+#pragma unroll
+                for (int u = 0; u < UQ; ++u) {
+                    const int idx = min(j + u, e - 1);
+                    c[u] = scol[idx];
+                    v[u] = sval[idx];
+                }
+#pragma unroll
+                for (int u = 0; u < UQ; ++u) { xr[u] = ld_coherent(rv + c[u]); xs[u] = ld_coherent(sv + c[u]); }
+#pragma unroll
+                for (int u = 0; u < UQ; ++u)
+                    if (j + u < e) acc = fma(v[u], fma(-alpha, xs[u], xr[u]), acc);
+                j += UQ;
+            }
+            if (valid) {
+                const double q_row = fma(-alpha, s_row, r_row);
+                a.v.y[row] = acc;
+                a.v.ax[row] = q_row;
+                dot[0] = fma(q_row, acc, dot[0]);
+                dot[1] = fma(acc, acc, dot[1]);
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+        }
+    }
+    __device__ void run_bicgstab_fq()
+    {
+        double d4[4], d2[2], d0[1];
+        if (stop_now()) return;
+        while (true) {
+            d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
+            spmv<EPI_RH_Y>(a.v.p, a.v.s, d4);                               // s = A p, (r#,s)
+            const bool ps = push(a.push_s);                                 // neighbours gather s in the next SpMV
+            { double t1[1] = {d4[0]}; barrier<1>(t1, with_halo(td_red(FIN_BICG_ALPHA, 1)), ps); }
+            if (stop_now()) break;
+            d4[0] = d4[1] = 0.0;
+            spmv_fq(__ldcg(&a.sc->alpha), d4);                              // y = A (r - alpha s), q -> ax
+            d2[0] = d4[0]; d2[1] = d4[1];
+            barrier<2>(d2, td_red(FIN_BICG_OMEGA, 2));
+            d2[0] = d2[1] = 0.0;
+            vec<PH_BICG_XR_Q>(d2);                                          // x, r = q - omega y, (r,r), (r#,r)
+            const bool pr = push(a.push_r);
+            barrier<2>(d2, with_halo(td_red(FIN_BICG_BETA, 2)), pr);
+            if (stop_now()) break;
+            vec<PH_BICG_P>(d0);                                             // p
+            const bool pp = push(a.push_p);
+            barrier<0>(d0, with_halo(td_none()), pp);
+        }
+    }
     // ---------------------------------------------------------------- solver.c:216-259 ----------------------
     __device__ void run_ca()
     {
@@ -314,7 +391,7 @@ struct Mega {
     }
 };
 
-template <int CT>
+template <int CT, bool FQ>
 __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_constant__ MegaArgs a)
 {
     using M = Mega<CT>;
@@ -385,7 +462,8 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
         m.s_flags = s_flags; m.tid = tid; m.t0 = t0; m.my_tiles = my_tiles; m.vis = 0u; m.stage_bytes = stage_bytes;
         m.row_lo = a.tile_row[t0]; m.row_hi = a.tile_row[t1]; m.failed = false;
         m.my_gen = ld_acquire_gpu(&a.bar->gen);       // left by the previous solve; nobody can have advanced it yet
-        if (a.method == 0) m.run_bicgstab();
+        if constexpr (FQ) m.run_bicgstab_fq();
+        else if (a.method == 0) m.run_bicgstab();
         else if (a.method == 1) m.run_ca();
         else m.run_pipe();
         cbar(CT);
@@ -393,19 +471,19 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
     }
 }
 
-template <int CT>
+template <int CT, bool FQ>
 cudaError_t launch(const MegaArgs &a, int grid, size_t smem, cudaStream_t st)
 {
     void *params[1] = {(void *)&a};
-    return cudaLaunchCooperativeKernel((const void *)bicg_mega_kernel<CT>, dim3(grid), dim3(CT + 32), params, smem, st);
+    return cudaLaunchCooperativeKernel((const void *)bicg_mega_kernel<CT, FQ>, dim3(grid), dim3(CT + 32), params, smem, st);
 }
-template <int CT>
+template <int CT, bool FQ>
 cudaError_t set_attr()
 {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, bicg_mega_kernel<CT>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, bicg_mega_kernel<CT, FQ>);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(bicg_mega_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(bicg_mega_kernel<CT, FQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 227 * 1024 - (int)fa.sharedSizeBytes);
 }
 
@@ -416,16 +494,18 @@ size_t mega_smem_bytes(int cap, int stages, int threads) { return (size_t)stages
 int mega_setup_attributes()
 {
     cudaError_t e;
-    if ((e = set_attr<256>()) != cudaSuccess) return (int)e;
-    if ((e = set_attr<512>()) != cudaSuccess) return (int)e;
+    if ((e = set_attr<256, false>()) != cudaSuccess) return (int)e;
+    if ((e = set_attr<512, false>()) != cudaSuccess) return (int)e;
+    if ((e = set_attr<256, true>()) != cudaSuccess) return (int)e;
+    if ((e = set_attr<512, true>()) != cudaSuccess) return (int)e;
     return 0;
 }
 
-int launch_mega(int threads, int grid, size_t smem, const MegaArgs &a, cudaStream_t st)
+int launch_mega(int threads, bool fuse_q, int grid, size_t smem, const MegaArgs &a, cudaStream_t st)
 {
     switch (threads) {
-    case 256: return (int)launch<256>(a, grid, smem, st);
-    case 512: return (int)launch<512>(a, grid, smem, st);
+    case 256: return (int)(fuse_q ? launch<256, true>(a, grid, smem, st) : launch<256, false>(a, grid, smem, st));
+    case 512: return (int)(fuse_q ? launch<512, true>(a, grid, smem, st) : launch<512, false>(a, grid, smem, st));
     default:  return (int)cudaErrorInvalidValue;
     }
 }

@@ -30,7 +30,8 @@ struct MegaArgs {
     unsigned long long *trace;  // optional [MEGA_TRACE_ITERS][MEGA_TRACE_SLOTS] globaltimer checkpoints of CTA 0 (BICG_MEGA_TRACE)
 };
 
-int    launch_mega(int threads, int grid, size_t smem, const MegaArgs &a, cudaStream_t st);
+// fuse_q: experimental 4-barrier BiCGStab (q gathered on the fly in the second SpMV), bicgstab only
+int    launch_mega(int threads, bool fuse_q, int grid, size_t smem, const MegaArgs &a, cudaStream_t st);
 int    mega_setup_attributes();
 size_t mega_smem_bytes(int cap, int stages, int threads);
 

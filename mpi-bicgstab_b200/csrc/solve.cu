@@ -91,7 +91,8 @@ struct Seq {
         a.push_z = make_push(V_Z); a.push_w = make_push(V_W);
         a.method = method;
         a.trace = m->d_trace;
-        int rc = launch_mega(m->mega.threads, m->mega.grid, m->mega.smem, a, c.stream);
+        const bool fq = c.cfg.mega_fuseq && method == BICG_METHOD_BICGSTAB;
+        int rc = launch_mega(m->mega.threads, fq, m->mega.grid, m->mega.smem, a, c.stream);
         if (rc) {
             // e.g. the grid cannot be co-resident because something else holds SMs: not an error, the
             // kernel-per-phase path below does the same job
@@ -148,6 +149,7 @@ struct Seq {
         vec(PH_PUSH, tail_none(), V_X);
         spmv(V_X, V_AX, tail_none());                                            // Ax = A x0
         vec(PH_BICG_INIT, tail_allreduce(FIN_BICG_INIT, 1), V_P);                // r, r#, p, (r,r)
+        if (c.cfg.mega_fuseq && c.cfg.mega && m->mega.ok) vec(PH_PUSH, tail_none(), V_R);   // experimental loop gathers r too
     }
     // ---- solver.c:88-120 -------------------------------------------------------------------------------
     void bicgstab_iter()

@@ -46,6 +46,7 @@ enum Phase : int {
     PH_RR_R,            // r=b-Ax                                    [push r]
     PH_RR_DOTS,         // 5 dots                                    [push w]
     PH_PUSH,            // push only
+    PH_BICG_XR_Q,       // like PH_BICG_XR with q in its own vector (ax) -- experimental 4-barrier loop of mega.cu
     PH_COUNT
 };
 
