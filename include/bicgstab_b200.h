@@ -162,6 +162,11 @@ void bicg_plan_partition(int n, int world, int *counts, int *displs);          /
  * or -2 if a single row exceeds cap_nnz. */
 int  bicg_plan_tiles(const unsigned int *ptr, int rows, int rows_per_tile, int cap_nnz, int *tile_row,
                      int tile_row_cap);
+/* Tile plan of the persistent solver kernel: CTA g of `ctas` owns rows [rows*g/ctas, rows*(g+1)/ctas), cut into tiles of
+ * <= threads rows of equal height.  tile_row[0..ntiles] (first row of each tile, then `rows`), cta_tile[0..ctas] (first
+ * tile of each CTA).  Returns ntiles (or -needed ints), *max_tile_nnz = entries of the fullest tile. */
+int  bicg_plan_cta_tiles(const unsigned int *ptr, int rows, int ctas, int threads, int *tile_row, int tile_row_cap,
+                         int *cta_tile, unsigned int *max_tile_nnz);
 /* Halo plan of rank `self`: which global columns of the offd block it must receive, as merged runs.
  * runs_out holds triples (first_col, length, owner); returns the number of runs (or -needed if cap is small).
  * gap: runs of one owner separated by <= gap unreferenced columns are merged. */

@@ -370,21 +370,8 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr)
     const long long SMEM_MAX = 224 * 1024;
     for (int threads : {512, 256}) {
         if (c.cfg.mega_threads && c.cfg.mega_threads != threads) continue;
-        std::vector<int> tile_row, cta_tile((size_t)G + 1);
-        unsigned max_tile_nnz = 0;
-        for (int g = 0; g < G; ++g) {
-            const long long lo = (long long)m->n_loc * g / G, hi = (long long)m->n_loc * (g + 1) / G;
-            cta_tile[(size_t)g] = (int)tile_row.size();
-            const int len = (int)(hi - lo);
-            const int k = (len + threads - 1) / threads;
-            for (int t = 0; t < k; ++t) {
-                const int r0 = (int)(lo + (long long)len * t / k), r1 = (int)(lo + (long long)len * (t + 1) / k);
-                tile_row.push_back(r0);
-                max_tile_nnz = std::max(max_tile_nnz, h_ptr[r1] - h_ptr[r0]);
-            }
-        }
-        cta_tile[(size_t)G] = (int)tile_row.size();
-        tile_row.push_back(m->n_loc);
+        std::vector<int> tile_row, cta_tile;
+        const unsigned max_tile_nnz = plan_cta_tiles(h_ptr, m->n_loc, G, threads, tile_row, cta_tile);   // plan.cpp
         const int cap = round_up((long long)max_tile_nnz + 8, 32);
         const long long stage = (long long)cap * 12 + (long long)(threads + 8) * 4;
         int stages = (int)std::min<long long>(4, SMEM_MAX / stage);

@@ -101,6 +101,32 @@ void merge_blocks(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Mat
     }
 }
 
+// Tile plan of the persistent solver kernel (mega.cu): CTA g of `ctas` owns the contiguous rows
+// [rows*g/ctas, rows*(g+1)/ctas), cut into ceil(len/threads) tiles of (almost) equal height.  tile_row gets the first
+// row of every tile plus a final `rows`; cta_tile[g] is the index of CTA g's first tile (cta_tile[ctas] = #tiles).
+// Returns the largest number of entries in any tile.
+unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int threads, std::vector<int> &tile_row,
+                        std::vector<int> &cta_tile)
+{
+    tile_row.clear();
+    cta_tile.assign((size_t)ctas + 1, 0);
+    unsigned max_tile_nnz = 0;
+    for (int g = 0; g < ctas; ++g) {
+        const long long lo = (long long)rows * g / ctas, hi = (long long)rows * (g + 1) / ctas;
+        cta_tile[(size_t)g] = (int)tile_row.size();
+        const int len = (int)(hi - lo);
+        const int k = (len + threads - 1) / threads;
+        for (int t = 0; t < k; ++t) {
+            const int r0 = (int)(lo + (long long)len * t / k), r1 = (int)(lo + (long long)len * (t + 1) / k);
+            tile_row.push_back(r0);
+            max_tile_nnz = std::max(max_tile_nnz, ptr[r1] - ptr[r0]);
+        }
+    }
+    cta_tile[(size_t)ctas] = (int)tile_row.size();
+    tile_row.push_back(rows);
+    return max_tile_nnz;
+}
+
 // From every rank's receive list (quadruples first_col, len, owner, ghost_idx; `stride` ints per rank, cnts[p]
 // valid quadruples) derive what rank `self` must push to rank `dest`: local source run -> ghost offset on dest.
 void plan_push_runs(const int *all_recv, const int *cnts, int stride, int self, int dest, int my_first,
@@ -140,6 +166,18 @@ extern "C" long long bicg_plan_merge(const CSR_Matrix *diag, const CSR_Matrix *o
     std::memcpy(recv_out, recv.data(), recv.size() * sizeof(int));
     *n_ghost_out = n_ghost;
     return (long long)(recv.size() / 4);
+}
+
+extern "C" int bicg_plan_cta_tiles(const unsigned int *ptr, int rows, int ctas, int threads, int *tile_row, int tile_row_cap,
+                                   int *cta_tile, unsigned int *max_tile_nnz)
+{
+    std::vector<int> tr, ct;
+    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, threads, tr, ct);
+    if ((int)tr.size() > tile_row_cap) return -(int)tr.size();
+    std::memcpy(tile_row, tr.data(), tr.size() * sizeof(int));
+    std::memcpy(cta_tile, ct.data(), ct.size() * sizeof(int));
+    if (max_tile_nnz) *max_tile_nnz = mx;
+    return (int)tr.size() - 1;
 }
 
 extern "C" int bicg_plan_tiles(const unsigned int *ptr, int rows, int rows_per_tile, int cap_nnz,

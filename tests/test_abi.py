@@ -183,3 +183,23 @@ def test_options_and_unknown_keys(B):
         B.set_option("NO_SUCH_OPTION", 1)
     B.set_options(tol=1e-15, max_iter=1000, out_iter=100, unroll=10, graph=1)
     assert B.lib.bicg_comm_rank() == 0 and B.lib.bicg_comm_world() == 1 and B.lib.bicg_comm_selftest() == 0
+
+
+@pytest.mark.parametrize("rows,ctas,threads", [(1601613, 148, 512), (200264, 148, 512), (343, 148, 512), (1, 148, 256),
+                                                (5000, 7, 256), (148 * 512, 148, 512)])
+def test_persistent_kernel_tile_plan(B, rows, ctas, threads):
+    """plan_cta_tiles (mega.cu's work split): contiguous, complete, balanced, every tile fits the CTA's threads."""
+    rng = np.random.default_rng(rows)
+    ptr = np.concatenate([[0], np.cumsum(rng.integers(0, 20, size=rows))]).astype(np.uint32)
+    cap = rows + ctas + 8
+    tr = (C.c_int * cap)(); ct = (C.c_int * (ctas + 1))(); mx = C.c_uint()
+    nt = B.lib.bicg_plan_cta_tiles(ptr.ctypes.data_as(C.POINTER(C.c_uint)), rows, ctas, threads, tr, cap, ct, C.byref(mx))
+    t = np.array(tr[:nt + 1]); c = np.array(ct[:])
+    assert t[0] == 0 and t[-1] == rows and np.all(np.diff(t) > 0) and np.all(np.diff(t) <= threads)
+    assert c[0] == 0 and c[-1] == nt and np.all(np.diff(c) >= 0)
+    per_cta = t[c[1:]] - t[c[:-1]]                               # rows owned by every CTA
+    assert per_cta.sum() == rows and per_cta.max() - per_cta.min() <= 1
+    for g in range(ctas):                                        # tiles of one CTA have (almost) equal height
+        h = np.diff(t[c[g]:c[g + 1] + 1])
+        assert h.size == 0 or h.max() - h.min() <= 1
+    assert mx.value == (ptr[t[1:]].astype(np.int64) - ptr[t[:-1]].astype(np.int64)).max()
