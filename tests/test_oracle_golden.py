@@ -46,6 +46,23 @@ def test_oracle_against_compiled_reference_live(B, O):
         assert np.array_equal(o["x"], r["x"]) and np.array_equal(o["r"], r["r"])
 
 
+def test_oracle_rhs_ones_multi_rank_live(B, O, tmp_path):
+    """README / BASELINE wording "right-hand side = all ones" (main.c itself uses b = A*1): the oracle follows the
+    compiled reference for that rhs too, with 1 and 3 ranks."""
+    if not O.have_ref("ref_driver_strict"):
+        pytest.skip("oracle/_ref not built on this box")
+    blk, n, ptr, col, val = global_csr(B, "stencil15", 9, 14.0)
+    f = str(tmp_path / "a.bin")
+    O.write_csr_bin(f, n, ptr, col, val)
+    for P in (1, 3):
+        for method in METHODS[:3]:
+            o = O.solve(method, n, ptr, col, val, np.ones(n), P=P, tol=1e-11, max_iter=400)
+            r = O.ref_driver(method, f, P=P, rhs="ones", tol=1e-11, max_iter=400, flavour="strict")
+            assert o["iters"] == r["iters"]
+            assert np.array_equal(np.sqrt(o["hist"][1:]), r["res"])
+            assert np.array_equal(o["x"], r["x"]) and np.array_equal(o["r"], r["r"])
+
+
 def test_oracle_spmv_and_blas1(B, O):
     blk, n, ptr, col, val = global_csr(B, "random", 500, 6)
     import scipy.sparse as sp
