@@ -41,7 +41,7 @@ struct Config {
     int mega = 1;                // 1: persistent cooperative kernel for the iteration loop where applicable
     int mega_threads = 0;        // 0 choose (512, else 256)
     int mega_trace = 0;
-    int mega_fuseq = 0;          // EXPERIMENTAL 4-barrier BiCGStab in the persistent kernel (not validated yet)
+    int mega_fuseq = 0;          // EXPERIMENTAL 4-barrier BiCGStab in the persistent kernel (1-GPU parity only so far)
     int device = -1;
     int halo_gap = 64;
     int verbose = 0;

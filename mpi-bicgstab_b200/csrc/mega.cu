@@ -265,7 +265,7 @@ struct Mega {
             ++trace_it;
         }
     }
-    // EXPERIMENTAL (BICG_MEGA_FUSEQ=1, off by default, not yet validated on hardware): y = A q with
+    // EXPERIMENTAL (BICG_MEGA_FUSEQ=1, off by default; parity-green on one GPU, not yet timed, not yet run multi-GPU): y = A q with
     // q[col] = r[col] - alpha s[col] gathered on the fly (solver.c:94 folded into :96), q[row] written to the spare
     // vector ax, dots (q,y), (y,y).  Removes the q vector phase and one grid barrier per iteration.
     __device__ void spmv_fq(double alpha, double (&dot)[4])
