@@ -142,6 +142,19 @@ int bicg_spmv_time(bicg_matrix *m, int reps, double *ms, double *bytes);
  * classes: 0 = SpMV(+dots), 1 = fused vector updates, 2 = other.  ms are totals over the solve. */
 int bicg_profile_solve(bicg_matrix *m, int method, int iters, double class_ms[3], int class_launches[3]);
 
+/* Test hooks for kernel-level parity (tests/test_gpu_kernels.py); single rank.  `vecs` holds the 11 arena vectors
+ * x r r# p s y|z w v t b ax (n_loc doubles each), in and out.
+ *   bicg_debug_vec_phase: ONE fused vector phase (enum Phase of csrc/vec.cuh) with coef = {alpha, beta, omega}; returns the
+ *                         number of dot products the phase reduces, their values in dots[].
+ *   bicg_debug_spmv_epi : s = A p with the solver's epilogue dots (1: (r#,s); 2: (r,s),(s,s); 3: w = A p with
+ *                         (r#,r),(r#,w),(r#,ax),(r#,z)).
+ *   bicg_debug_get_vec / _get_scalars: arena vector `id` / {rTr rTr_old rTs rTy yTy rTw wTw rTz dot_r dot_zero alpha
+ *                         beta omega} as the last solve on this handle left them. */
+int bicg_debug_vec_phase(bicg_matrix *m, int phase, const double coef[3], double *vecs, double dots[8]);
+int bicg_debug_spmv_epi(bicg_matrix *m, int epi, double *vecs, double dots[8]);
+int bicg_debug_get_vec(bicg_matrix *m, int id, double *out);
+int bicg_debug_get_scalars(bicg_matrix *m, double out[13]);
+
 /* full-precision history of the last solve on this rank: out[k] = dot_r/dot_zero after iteration k
  * (out[0] = 1).  Returns the number of entries available (iters + 1). */
 int bicg_last_history(double *out, int cap);
@@ -162,11 +175,12 @@ void bicg_plan_partition(int n, int world, int *counts, int *displs);          /
  * or -2 if a single row exceeds cap_nnz. */
 int  bicg_plan_tiles(const unsigned int *ptr, int rows, int rows_per_tile, int cap_nnz, int *tile_row,
                      int tile_row_cap);
-/* Tile plan of the persistent solver kernel: CTA g of `ctas` owns rows [rows*g/ctas, rows*(g+1)/ctas), cut into tiles of
- * <= threads rows of equal height.  tile_row[0..ntiles] (first row of each tile, then `rows`), cta_tile[0..ctas] (first
- * tile of each CTA).  Returns ntiles (or -needed ints), *max_tile_nnz = entries of the fullest tile. */
-int  bicg_plan_cta_tiles(const unsigned int *ptr, int rows, int ctas, int threads, int *tile_row, int tile_row_cap,
-                         int *cta_tile, unsigned int *max_tile_nnz);
+/* Tile plan of the persistent solver kernel: CTA g of `ctas` owns a contiguous row range starting at a multiple of 16
+ * rows; ranges are balanced by per-row work 24*nnz(row) + 216 + extra_weight*row_extra[row] (row_extra may be NULL) and
+ * cut into tiles of <= rows_per_tile rows of equal height.  tile_row[0..ntiles] (first row of each tile, then `rows`),
+ * cta_tile[0..ctas] (first tile of each CTA).  Returns ntiles (or -needed ints), *max_tile_nnz = entries of the fullest tile. */
+int  bicg_plan_cta_tiles(const unsigned int *ptr, int rows, int ctas, int rows_per_tile, const unsigned char *row_extra,
+                         int extra_weight, int *tile_row, int tile_row_cap, int *cta_tile, unsigned int *max_tile_nnz);
 /* Halo plan of rank `self`: which global columns of the offd block it must receive, as merged runs.
  * runs_out holds triples (first_col, length, owner); returns the number of runs (or -needed if cap is small).
  * gap: runs of one owner separated by <= gap unreferenced columns are merged. */

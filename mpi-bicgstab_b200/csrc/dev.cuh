@@ -38,11 +38,11 @@ struct Scalars {
     unsigned int pad_;
 };
 
-// one mailbox = what rank `src` contributes to one reduction: eight 16-byte slots {value, epoch}.  A slot is written
-// with ONE 16-byte store, so value and epoch arrive together and the receiver needs no fence between "flag" and
-// data (the LL idea of NCCL); 128 B so that no two mailboxes share a line.
-struct alignas(16) LLSlot { double v; unsigned long long ep; };
-struct alignas(128) Mailbox { LLSlot s[MAIL_VALS]; };
+// one mailbox = what rank `src` contributes to one reduction: MAIL_VALS doubles, each as TWO self-validating 8-byte
+// words {flag32 | data32} (NCCL's LL protocol): an aligned 8-byte store is single-copy atomic, so a word whose flag
+// equals the expected epoch carries valid data -- no fence between "flag" and data, and nothing depends on a 16-byte
+// vector store arriving un-torn over NVLink.  128 B so that no two mailboxes share a line.
+struct alignas(128) Mailbox { unsigned long long w[2 * MAIL_VALS]; };
 struct alignas(128) HaloFlag { unsigned long long epoch; unsigned long long pad_[15]; };
 
 // peer-memory view of the job, passed by value to every kernel
@@ -156,15 +156,63 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_ll(LLSlot *p, double v, unsigned long long ep)
+// ---- LL words: {flag32 | data32}; a double travels as two of them ------------------------------------------
+__device__ __forceinline__ unsigned long long ll_pack(unsigned data, unsigned flag)
 {
-    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(ep) : "memory");
+    return ((unsigned long long)flag << 32) | (unsigned long long)data;
 }
-__device__ __forceinline__ void ld_ll(const LLSlot *p, double &v, unsigned long long &ep)
+__device__ __forceinline__ void ll_encode(double v, unsigned flag, unsigned long long &w0, unsigned long long &w1)
 {
-    long long vb;
-    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(vb), "=l"(ep) : "l"(p) : "memory");
-    v = __longlong_as_double(vb);
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    w0 = ll_pack((unsigned)b, flag);
+    w1 = ll_pack((unsigned)(b >> 32), flag);
+}
+__device__ __forceinline__ bool ll_valid(unsigned long long w0, unsigned long long w1, unsigned flag)
+{
+    return (unsigned)(w0 >> 32) == flag && (unsigned)(w1 >> 32) == flag;
+}
+__device__ __forceinline__ double ll_decode(unsigned long long w0, unsigned long long w1)
+{
+    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+// both words of one value with one 16-byte access; each word validates itself, so tearing is harmless
+__device__ __forceinline__ void st_ll_sys(unsigned long long *p, unsigned long long w0, unsigned long long w1)
+{
+    asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ void ld_ll_sys(const unsigned long long *p, unsigned long long &w0, unsigned long long &w1)
+{
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_ll_gpu(unsigned long long *p, unsigned long long w)
+{
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_ll_gpu(const unsigned long long *p)
+{
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
+}
+__device__ __forceinline__ void ld_ll_gpu2(const unsigned long long *p, unsigned long long &w0, unsigned long long &w1)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// plain ld.global: L1-cached but never the non-coherent (.nc) path -- for vectors that other SMs / peer GPUs rewrite
+// while the kernel is running (visibility comes from the acquire fence that follows the flag wait)
+__device__ __forceinline__ double ld_coherent(const double *p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ double ld_volatile_f64(const double *p)
 {
@@ -217,19 +265,23 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double *scratch)
 // ------------------------------------------------------------------------------------------------
 // cross-GPU reduction over peer mailboxes (called by warp 0 of the last CTA, all 32 lanes)
 // ------------------------------------------------------------------------------------------------
-// post: lane p stores this rank's `nv` values (at least one slot, so a pure barrier works too) into rank p's
-// mailbox[parity][me], each as one {value, epoch} store.
+// post: lane p stores this rank's `nv` values (at least one, so a pure barrier works too) into rank p's
+// mailbox[parity][me] as LL words carrying the epoch.
 __device__ __forceinline__ void xg_post(const CommDev &c, unsigned epoch, const double *vals, int nv)
 {
     const int lane = threadIdx.x & 31;
     if (lane < c.world) {
         Mailbox *mb = c.mail[lane] + (epoch & 1u) * MAX_RANKS + c.rank;
         const int n = nv > 0 ? nv : 1;
-        for (int k = 0; k < n; ++k) st_ll(&mb->s[k], nv > 0 ? vals[k] : 0.0, (unsigned long long)epoch);
+        for (int k = 0; k < n; ++k) {
+            unsigned long long w0, w1;
+            ll_encode(nv > 0 ? vals[k] : 0.0, epoch, w0, w1);
+            st_ll_sys(&mb->w[2 * k], w0, w1);
+        }
     }
     __syncwarp();
 }
-// wait: lane p polls the slots rank p sent to this rank until they carry `epoch`, keeps rank p's values; lane k
+// wait: lane p polls the words rank p sent to this rank until they carry `epoch`, keeps rank p's values; lane k
 // then adds value k over ranks 0..world-1 in rank order (the same order on every rank -> bitwise identical
 // results everywhere).  Returns false on timeout.
 __device__ __forceinline__ bool xg_wait_sum(const CommDev &c, unsigned epoch, double *vals, int nv)
@@ -242,13 +294,13 @@ __device__ __forceinline__ bool xg_wait_sum(const CommDev &c, unsigned epoch, do
         const unsigned long long t0 = globaltimer_ns();
         const int n = nv > 0 ? nv : 1;
         for (int k = 0; k < n && ok; ++k) {
-            double v; unsigned long long ep;
+            unsigned long long w0, w1;
             for (;;) {
-                ld_ll(&mine[lane].s[k], v, ep);
-                if (ep >= (unsigned long long)epoch) break;
+                ld_ll_sys(&mine[lane].w[2 * k], w0, w1);
+                if (ll_valid(w0, w1, epoch)) break;
                 if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
             }
-            s_contrib[lane][k] = v;
+            s_contrib[lane][k] = ll_decode(w0, w1);
         }
     }
     ok = __all_sync(0xffffffffu, ok);
@@ -275,12 +327,15 @@ __device__ __forceinline__ void loop_test(Scalars *s)
     }
 }
 
+// hist == nullptr: the caller keeps a private copy of the scalars and somebody else records the history
 __device__ __forceinline__ void finalize(int fin, Scalars *s, double *hist, const double *t)
 {
+    double hdummy;
+#define BICG_HIST(i) (*(hist ? &hist[i] : &hdummy))
     switch (fin) {
     case FIN_BICG_INIT:
         s->rTr = t[0]; s->dot_r = t[0]; s->dot_zero = t[0]; s->k = 0;         // solver.c:78-83
-        hist[0] = s->dot_r / s->dot_zero;
+        BICG_HIST(0) = s->dot_r / s->dot_zero;
         loop_test(s);
         break;
     case FIN_BICG_ALPHA:
@@ -297,7 +352,7 @@ __device__ __forceinline__ void finalize(int fin, Scalars *s, double *hist, cons
         s->rTr = t[1];
         s->beta = (s->alpha / s->omega) * (s->rTr / s->rTr_old);              // solver.c:116
         s->k += 1;
-        hist[s->k] = s->dot_r / s->dot_zero;
+        BICG_HIST(s->k) = s->dot_r / s->dot_zero;
         loop_test(s);
         break;
     case FIN_STORE_RTR:
@@ -308,7 +363,7 @@ __device__ __forceinline__ void finalize(int fin, Scalars *s, double *hist, cons
         s->alpha = s->rTr / s->rTw;                                           // solver.c:210
         s->beta = 0.0; s->omega = 0.0;                                        // :211 (omega pinned)
         s->dot_r = s->rTr; s->dot_zero = s->rTr; s->k = 0;                    // :212-213
-        hist[0] = s->dot_r / s->dot_zero;
+        BICG_HIST(0) = s->dot_r / s->dot_zero;
         loop_test(s);
         break;
     case FIN_OMEGA2:
@@ -322,11 +377,12 @@ __device__ __forceinline__ void finalize(int fin, Scalars *s, double *hist, cons
         s->beta = (s->alpha / s->omega) * (s->rTr / s->rTr_old);              // :248
         s->alpha = s->rTr / (s->rTw + s->beta * (s->rTs - s->omega * s->rTz)); // :249
         s->k += 1;
-        hist[s->k] = s->dot_r / s->dot_zero;
+        BICG_HIST(s->k) = s->dot_r / s->dot_zero;
         loop_test(s);
         break;
     default: break;
     }
+#undef BICG_HIST
 }
 
 // Wait until every peer in recv_mask has published halo epoch >= `expect` (called by warp 0 of a CTA).
@@ -403,11 +459,11 @@ __device__ __forceinline__ void tail_warp(const KernelCommon &kc, double (&tot)[
     if (td.signal_halo) {
         // all CTAs fenced their peer stores before taking a ticket; publish the new epoch to receivers
         const unsigned he = sc->halo_epoch + 1u;
-        // no fence here: every CTA that pushed fenced at system scope BEFORE its ticket / barrier arrival, this warp
-        // observed all arrivals (acquire) before getting here, so the halo data is already visible system-wide; a
-        // plain system-scope store of the flag is enough (a release store would cost another NVLink round trip)
+        // every CTA that pushed fenced at system scope BEFORE its ticket, and this warp observed all tickets; the
+        // flag itself is a system-scope RELEASE store so the pattern is a proper release chain at system scope
+        // (one warp per kernel pays for it)
         if (lane < kc.comm.world && ((kc.comm.send_mask >> lane) & 1u))
-            st_flag_sys(&kc.comm.hflag[lane][kc.comm.rank].epoch, (unsigned long long)he);
+            st_release_sys(&kc.comm.hflag[lane][kc.comm.rank].epoch, (unsigned long long)he);
         __syncwarp();
         if (wait_halo && !halo_wait_epoch(kc.comm, he) && lane == 0) { sc->error = 1; sc->done = 1; }
         if (lane == 0) sc->halo_epoch = he;

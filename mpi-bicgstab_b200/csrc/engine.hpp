@@ -41,7 +41,9 @@ struct Config {
     int mega = 1;                // 1: persistent cooperative kernel for the iteration loop where applicable
     int mega_threads = 0;        // 0 choose (512, else 256)
     int mega_trace = 0;
-    int mega_fuseq = 0;          // EXPERIMENTAL 4-barrier BiCGStab in the persistent kernel (1-GPU parity only so far)
+    int mega_lanes = 0;          // lanes per row of the persistent kernel's SpMV (0 choose from the mean row length)
+    int l2_hint = 1;             // matrix stream loaded with an L2 evict-first policy (persistent kernel)
+    int boundary_weight = 600;   // extra work (bytes) charged per pushed row when CTA row ranges are balanced
     int device = -1;
     int halo_gap = 64;
     int verbose = 0;
@@ -100,9 +102,6 @@ Context &ctx();
 void load_config_from_env(Config &c);
 int  set_option(Config &c, const char *key, const char *value);
 
-enum VecId { V_X = 0, V_R, V_RH, V_P, V_S, V_Y, V_W, V_V, V_T, V_B, V_AX, V_COUNT };
-// V_Y doubles as z (the CA / pipelined variants call the same storage z)
-constexpr int V_Z = V_Y;
 
 struct SpmvPlan {
     int kind = 0, lanes = 1, threads = 256, stages = 3, cap = 0, grid = 0, ctas_per_sm = 1;
@@ -115,12 +114,14 @@ struct SpmvPlan {
 
 struct MegaPlan {
     bool ok = false;
-    int threads = 512, stages = 2, cap = 0, grid = 0;
+    int threads = 512, lanes = 1, stages = 2, cap = 0, grid = 0;
     size_t smem = 0;
     int ntiles = 0;
     int *d_tile_row = nullptr;
     unsigned *d_tile_nz = nullptr;
     int *d_cta_tile = nullptr;
+    int4 *d_cta_dep = nullptr;
+    std::vector<int> cta_row;    // grid + 1: first row of every CTA
 };
 
 } // namespace bicg
@@ -138,7 +139,9 @@ struct bicg_matrix {
     unsigned *d_ptr = nullptr;
     bicg::SpmvPlan plan;
     bicg::MegaPlan mega;             // persistent-kernel plan (mega.cu)
-    bicg::GridBar *d_bar = nullptr;
+    bicg::MegaSync *d_msync = nullptr;
+    bicg::MegaSync *peer_msync[bicg::MAX_RANKS] = {};
+    int *d_ghost_first = nullptr;
     unsigned long long *d_trace = nullptr;   // BICG_MEGA_TRACE
     // ghost layout
     int ghost_off = 0;           // first ghost column index = roundup(n_loc, 16)

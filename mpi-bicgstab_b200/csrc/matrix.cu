@@ -51,7 +51,9 @@ int set_option(Config &c, const char *key, const char *value)
     else if (k == "MEGA") c.mega = as_int();
     else if (k == "MEGA_THREADS") c.mega_threads = as_int();
     else if (k == "MEGA_TRACE") c.mega_trace = as_int();
-    else if (k == "MEGA_FUSEQ") c.mega_fuseq = as_int();
+    else if (k == "MEGA_LANES") c.mega_lanes = as_int();
+    else if (k == "L2_HINT") c.l2_hint = as_int();
+    else if (k == "BOUNDARY_WEIGHT") c.boundary_weight = std::max(0, as_int());
     else if (k == "DEVICE") c.device = as_int();
     else if (k == "HALO_GAP") c.halo_gap = std::max(0, as_int());
     else if (k == "VERBOSE") c.verbose = as_int();
@@ -64,7 +66,7 @@ void load_config_from_env(Config &c)
 {
     static const char *keys[] = {"BICG_TOL", "BICG_MAX_ITER", "BICG_OUT_ITER", "BICG_QUIET", "BICG_SPMV",
                                  "BICG_SPMV_LANES", "BICG_SPMV_THREADS", "BICG_SPMV_STAGES", "BICG_SPMV_CTAS",
-                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_MEGA_FUSEQ", "BICG_DEVICE",
+                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_MEGA_LANES", "BICG_L2_HINT", "BICG_BOUNDARY_WEIGHT", "BICG_DEVICE",
                                  "BICG_HALO_GAP", "BICG_VERBOSE", "BICG_FENCE_WRITERS"};
     for (const char *k : keys)
         if (const char *v = getenv(k)) set_option(c, k, v);
@@ -357,40 +359,58 @@ static void choose_spmv_plan(bicg_matrix *m, const unsigned *h_ptr)
                 m->plan.kind, m->plan.lanes, m->plan.threads, m->plan.stages, m->plan.ctas_per_sm, m->plan.ms);
 }
 
-// Plan of the persistent solver kernel (mega.cu): one CTA per SM, every CTA owns a contiguous, equally sized range
-// of rows, cut into <= threads-row tiles of equal size.
-static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr)
+// lanes per row of the persistent kernel's SpMV (instantiated: 1, 4, 8, 32)
+static int mega_lanes_for(double mean_row)
+{
+    if (mean_row <= 20.0) return 1;
+    if (mean_row <= 40.0) return 4;
+    if (mean_row <= 128.0) return 8;
+    return 32;
+}
+
+// Plan of the persistent solver kernel (mega.cu): one CTA per SM, every CTA owns a contiguous, work-balanced range of rows
+// (plan.cpp: plan_cta_tiles), cut into tiles of <= threads / lanes rows.  row_extra[i] = number of peers row i is pushed to.
+static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::vector<unsigned char> &row_extra)
 {
     Context &c = ctx();
     MegaPlan &mp = m->mega;
     mp.ok = false;
     if (m->n_loc < 1) return;                       // the plan is always built; BICG_MEGA gates its use per solve
-    if (c.cfg.mega != 2 && heuristic_lanes(m->mean_row) != 1) return;   // long rows: sub-warp-per-row kernels (BICG_MEGA=2 forces)
-    const int G = c.sm_count;
-    const long long SMEM_MAX = 224 * 1024;
+    const int G = std::min(c.sm_count, MEGA_MAX_CTAS);
+    const long long SMEM_MAX = 222 * 1024;
+    const int lanes = c.cfg.mega_lanes > 0 ? c.cfg.mega_lanes : mega_lanes_for(m->mean_row);
     for (int threads : {512, 256}) {
         if (c.cfg.mega_threads && c.cfg.mega_threads != threads) continue;
+        if (!mega_has_variant(threads, lanes)) continue;
+        const int rpt = threads / lanes;
         std::vector<int> tile_row, cta_tile;
-        const unsigned max_tile_nnz = plan_cta_tiles(h_ptr, m->n_loc, G, threads, tile_row, cta_tile);   // plan.cpp
+        const unsigned max_tile_nnz = plan_cta_tiles(h_ptr, m->n_loc, G, rpt, row_extra.empty() ? nullptr : row_extra.data(),
+                                                     c.cfg.boundary_weight, tile_row, cta_tile);
         const int cap = round_up((long long)max_tile_nnz + 8, 32);
-        const long long stage = (long long)cap * 12 + (long long)(threads + 8) * 4;
+        const long long stage = (long long)cap * 12 + (long long)(rpt + 8) * 4;
         int stages = (int)std::min<long long>(4, SMEM_MAX / stage);
         if (stages < 2) continue;                       // rows too long for this tile height
         std::vector<unsigned> tile_nz(tile_row.size());
         for (size_t i = 0; i < tile_row.size(); ++i) tile_nz[i] = h_ptr[tile_row[i]];
-        mp.threads = threads; mp.stages = stages; mp.cap = cap; mp.grid = G;
-        mp.smem = mega_smem_bytes(cap, stages, threads);
+        mp.threads = threads; mp.lanes = lanes; mp.stages = stages; mp.cap = cap; mp.grid = G;
+        mp.smem = mega_smem_bytes(cap, stages, threads, lanes);
         mp.ntiles = (int)tile_row.size() - 1;
+        mp.cta_row.assign((size_t)G + 1, m->n_loc);
+        for (int g = 0; g <= G; ++g) mp.cta_row[(size_t)g] = tile_row[(size_t)cta_tile[(size_t)g]];
         mp.d_tile_row = (decltype(mp.d_tile_row))c.dev_alloc(tile_row.size() * sizeof(int));
         mp.d_tile_nz = (decltype(mp.d_tile_nz))c.dev_alloc(tile_nz.size() * sizeof(unsigned));
         mp.d_cta_tile = (decltype(mp.d_cta_tile))c.dev_alloc(cta_tile.size() * sizeof(int));
-        BICG_CUDA(cudaMemcpy(mp.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice));
-        BICG_CUDA(cudaMemcpy(mp.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-        BICG_CUDA(cudaMemcpy(mp.d_cta_tile, cta_tile.data(), cta_tile.size() * sizeof(int), cudaMemcpyHostToDevice));
+        mp.d_cta_dep = (decltype(mp.d_cta_dep))c.dev_alloc((size_t)G * sizeof(int4));
+        BICG_CUDA(cudaMemcpyAsync(mp.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        BICG_CUDA(cudaMemcpyAsync(mp.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+        BICG_CUDA(cudaMemcpyAsync(mp.d_cta_tile, cta_tile.data(), cta_tile.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        launch_mega_dep(m->d_col, m->d_ptr, mp.d_tile_row, mp.d_cta_tile, G, m->ghost_off, mp.d_cta_dep, c.stream);
+        BICG_CUDA(cudaGetLastError());
+        BICG_CUDA(cudaStreamSynchronize(c.stream));     // the host vectors die here
         mp.ok = true;
         if (c.cfg.verbose)
-            fprintf(stderr, "[bicg mega r%d] threads=%d stages=%d cap=%d tiles=%d smem=%zu\n", m->rank, threads, stages, cap,
-                    mp.ntiles, mp.smem);
+            fprintf(stderr, "[bicg mega r%d] threads=%d lanes=%d stages=%d cap=%d tiles=%d smem=%zu\n", m->rank, threads, lanes,
+                    stages, cap, mp.ntiles, mp.smem);
         return;
     }
 }
@@ -400,7 +420,7 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr)
 // ------------------------------------------------------------------------------------------------
 struct ArenaHdr {
     cudaIpcMemHandle_t handle;
-    long long vec_off, vstride, ghost_off, mail_off, hflag_off;
+    long long vec_off, vstride, ghost_off, mail_off, hflag_off, msync_off;
     int n_loc, n_ghost;
 };
 
@@ -480,7 +500,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     const size_t hist_off = off;  off = align(off + (size_t)m->hist_cap * sizeof(double));
     const size_t mail_off = off;  off = align(off + 2 * MAX_RANKS * sizeof(Mailbox));
     const size_t hflag_off = off; off = align(off + MAX_RANKS * sizeof(HaloFlag));
-    const size_t bar_off = off;   off = align(off + sizeof(GridBar));
+    const size_t msync_off = off; off = align(off + sizeof(MegaSync));
     m->arena_bytes = std::max<size_t>(off, (size_t)4 << 20);     // its own allocation granule: the IPC handle maps exactly this
     if (m->world > 1) {
         // exported through CUDA IPC: always a fresh allocation of its own (peers map and unmap exactly this one)
@@ -495,18 +515,20 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     m->d_hist = (double *)(m->arena + hist_off);
     m->d_mail = (Mailbox *)(m->arena + mail_off);
     m->d_hflag = (HaloFlag *)(m->arena + hflag_off);
-    m->d_bar = (GridBar *)(m->arena + bar_off);
+    m->d_msync = (MegaSync *)(m->arena + msync_off);
     BICG_CUDA(cudaStreamSynchronize(c.stream));            // arena zeroed before any peer may write into it
 
     lap("arena alloc + zero");
     // ---- peers: exchange arena handles + layouts, then the halo runs -------------------------------
     m->comm.rank = m->rank; m->comm.world = m->world;
-    for (int p = 0; p < MAX_RANKS; ++p) { m->comm.mail[p] = m->d_mail; m->comm.hflag[p] = m->d_hflag; }
+    for (int p = 0; p < MAX_RANKS; ++p) { m->comm.mail[p] = m->d_mail; m->comm.hflag[p] = m->d_hflag; m->peer_msync[p] = m->d_msync; }
+    std::vector<unsigned char> row_extra;                  // per row: number of peers it is pushed to
+    std::vector<std::vector<PushRunHost>> push_host;       // per push slot
     if (m->world > 1) {
         ArenaHdr mine{};
         BICG_CUDA(cudaIpcGetMemHandle(&mine.handle, m->arena));
         mine.vec_off = (long long)vec_off; mine.vstride = m->vstride; mine.ghost_off = m->ghost_off;
-        mine.mail_off = (long long)mail_off; mine.hflag_off = (long long)hflag_off;
+        mine.mail_off = (long long)mail_off; mine.hflag_off = (long long)hflag_off; mine.msync_off = (long long)msync_off;
         mine.n_loc = m->n_loc; mine.n_ghost = m->n_ghost;
         std::vector<ArenaHdr> all((size_t)m->world);
         c.host_allgather(&mine, all.data(), sizeof(ArenaHdr));
@@ -517,6 +539,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
             m->peer_ghost_off[p] = all[(size_t)p].ghost_off;
             m->comm.mail[p] = (Mailbox *)((char *)m->peer_base[p] + all[(size_t)p].mail_off);
             m->comm.hflag[p] = (HaloFlag *)((char *)m->peer_base[p] + all[(size_t)p].hflag_off);
+            m->peer_msync[p] = (MegaSync *)((char *)m->peer_base[p] + all[(size_t)p].msync_off);
         }
         // receive lists of every rank (variable length -> two rounds)
         int my_cnt = (int)(m->recv_runs.size() / 4);
@@ -528,6 +551,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
         c.host_allgather(send.data(), recv.data(), send.size() * sizeof(int));
 
         unsigned recv_mask = 0, send_mask = 0;
+        row_extra.assign((size_t)m->n_loc, 0);
         for (int i = 0; i < my_cnt; ++i) recv_mask |= 1u << m->recv_runs[4 * (size_t)i + 2];
         const int my_first = info->displs[m->rank];
         for (int p = 0; p < m->world; ++p) {
@@ -542,6 +566,9 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
             m->push_peer[slot] = p; m->push_nruns[slot] = (int)pr.size();
             m->d_push_runs[slot] = (PushRun *)c.dev_alloc(pr.size() * sizeof(PushRun));
             BICG_CUDA(cudaMemcpy(m->d_push_runs[slot], pr.data(), pr.size() * sizeof(PushRun), cudaMemcpyHostToDevice));
+            for (const PushRunHost &r : ph)
+                for (int i = r.src; i < r.src + r.len; ++i) if (row_extra[(size_t)i] < 255) ++row_extra[(size_t)i];
+            push_host.push_back(ph);
         }
         m->comm.recv_mask = recv_mask; m->comm.send_mask = send_mask;
     }
@@ -554,10 +581,39 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
 
     // ---- SpMV plan ------------------------------------------------------------------------------------
     choose_spmv_plan(m, h_ptr);
-    build_mega_plan(m, h_ptr);
+    build_mega_plan(m, h_ptr, row_extra);
+    {
+        // first ghost slot of every owner (slots are grouped by owner, owners ascending: plan.cpp merge_blocks)
+        std::vector<int> gf((size_t)m->world + 1, 0);
+        for (size_t i = 0; i + 3 < m->recv_runs.size(); i += 4) gf[(size_t)m->recv_runs[i + 2] + 1] += m->recv_runs[i + 1];
+        for (int p = 0; p < m->world; ++p) gf[(size_t)p + 1] += gf[(size_t)p];
+        m->d_ghost_first = (int *)c.dev_alloc(gf.size() * sizeof(int));
+        BICG_CUDA(cudaMemcpy(m->d_ghost_first, gf.data(), gf.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (m->world > 1) {
+        // tell every receiver which of my CTAs push to it (they wait for exactly those flags), and everybody whether
+        // my persistent-kernel plan is usable (the choice of loop implementation must be the same on all ranks)
+        for (int slot = 0; slot < m->npush; ++slot) {
+            unsigned mask[MEGA_MASK_WORDS + 3] = {};
+            if (m->mega.ok)
+                for (const PushRunHost &r : push_host[(size_t)slot])
+                    for (int g = 0; g < m->mega.grid; ++g)
+                        if (m->mega.cta_row[(size_t)g] < r.src + r.len && m->mega.cta_row[(size_t)g + 1] > r.src &&
+                            m->mega.cta_row[(size_t)g + 1] > m->mega.cta_row[(size_t)g])
+                            mask[g >> 5] |= 1u << (g & 31);
+            BICG_CUDA(cudaMemcpyAsync(&m->peer_msync[m->push_peer[slot]]->pusher_mask[m->rank][0], mask, sizeof(mask),
+                                      cudaMemcpyDefault, c.stream));
+            BICG_CUDA(cudaStreamSynchronize(c.stream));          // `mask` is a stack buffer
+        }
+        const int ok = m->mega.ok ? 1 : 0;
+        for (int p = 0; p < m->world; ++p)
+            BICG_CUDA(cudaMemcpyAsync(&m->peer_msync[p]->st.plan_ok[m->rank], &ok, sizeof(int), cudaMemcpyDefault, c.stream));
+        BICG_CUDA(cudaStreamSynchronize(c.stream));
+    }
     if (c.cfg.mega_trace) {
-        m->d_trace = (decltype(m->d_trace))c.dev_alloc((size_t)MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS * sizeof(unsigned long long));
-        BICG_CUDA(cudaMemset(m->d_trace, 0, (size_t)MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS * sizeof(unsigned long long)));
+        const size_t tb = (size_t)2 * MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS * sizeof(unsigned long long);
+        m->d_trace = (decltype(m->d_trace))c.dev_alloc(tb);
+        BICG_CUDA(cudaMemset(m->d_trace, 0, tb));
     }
 
     lap("spmv plan");
@@ -570,6 +626,9 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     if (m->world > 1) {          // nobody may start pushing before every rank has mapped every arena
         int token = 0; std::vector<int> all((size_t)m->world);
         c.host_allgather(&token, all.data(), sizeof(int));
+        int oks[MAX_RANKS] = {};
+        BICG_CUDA(cudaMemcpy(oks, m->d_msync->st.plan_ok, sizeof(oks), cudaMemcpyDeviceToHost));
+        for (int p = 0; p < m->world; ++p) if (!oks[p]) m->mega.ok = false;
     }
     return m;
 }
@@ -593,7 +652,8 @@ void matrix_destroy(bicg_matrix *m)
     for (int s = 0; s < m->npush; ++s) c.dev_free(m->d_push_runs[s]);
     free_plan(m->plan);
     c.dev_free(m->d_trace);
-    c.dev_free(m->mega.d_tile_row); c.dev_free(m->mega.d_tile_nz); c.dev_free(m->mega.d_cta_tile);
+    c.dev_free(m->mega.d_tile_row); c.dev_free(m->mega.d_tile_nz); c.dev_free(m->mega.d_cta_tile); c.dev_free(m->mega.d_cta_dep);
+    c.dev_free(m->d_ghost_first);
     if (m->hist_extra) cudaFree(m->hist_extra);
     c.dev_free(m->d_val); c.dev_free(m->d_col); c.dev_free(m->d_ptr); c.dev_free(m->arena);
     delete m;

@@ -1,23 +1,32 @@
 // mega.cu -- one persistent, cooperative kernel per solve: the whole iteration loop of solver.c on the device.
 //
-// Why: with the matrix split over 8 GPUs an iteration is ~13 us of memory traffic, and five kernel boundaries
-// (launch latency + last-CTA election + reduction tail each) cost several times that.  Here one CTA per SM stays
-// resident for the entire solve.  Every CTA owns a fixed, contiguous range of rows:
-//   * SpMV phases run the warp-specialised TMA pipeline of spmv.cu over the CTA's own tiles; the producer warp
-//     never stops -- while the consumers run a vector phase or sit in a barrier it is already streaming the first
-//     stages of the NEXT SpMV (the matrix never changes), so the DRAM pipe stays primed across phases;
-//   * vector phases touch only the CTA's own rows (same element-wise bodies as vec.cu), so nothing but the
-//     gathered x crosses SMs;
-//   * phases are separated by a grid barrier (atomic arrive + generation flag) whose last arriver -- the master
-//     warp -- combines the per-CTA dot partials in a fixed order, performs the cross-GPU reduction over the peer
-//     mailboxes, evaluates the scalar recurrence (dev.cuh: tail_warp, identical to the multi-kernel path), signals
-//     and awaits the neighbours' halo epochs, and only then opens the barrier.  The loop test of solver.c:86 is
-//     evaluated there too, so the kernel leaves the loop at exactly the reference's iteration.
-// Coherence: x is gathered with plain (L1-cached) loads; every thread-0 that observes the barrier opening issues a
-// gpu-scope fence (L1 invalidate) before its CTA continues, so rows rewritten by other SMs are re-fetched from L2.
+// Why: with the matrix split over 8 GPUs an iteration is ~13 us of memory traffic; kernel boundaries, atomics and
+// master/worker barriers cost several times that.  Here one CTA per SM stays resident for the entire solve and
+//   * owns a fixed, contiguous, work-balanced range of rows (plan.cpp: plan_cta_tiles_weighted);
+//   * runs the SpMV phases as the warp-specialised TMA pipeline of spmv.cu over its own tiles -- the producer warp
+//     never stops: while the consumers are in a vector phase or wait at a synchronisation point it is already
+//     streaming the first stages of the NEXT SpMV (the matrix never changes), with an L2 evict-first policy so that
+//     the once-per-SpMV matrix stream does not push the (re-used) vectors out of the 126 MB L2;
+//   * runs the vector phases (vec_body.cuh) on its own rows only, so nothing but the gathered x crosses SMs;
+//   * keeps ITS OWN copy of the solver scalars (alpha, beta, omega, the dots, k, the loop test) in shared memory:
+//     every CTA evaluates the recurrences of solver.c:93-120 itself from the same reduced values, in the same
+//     order, so all CTAs (and all ranks) take bitwise identical decisions and nobody waits for a "master".
 //
-// Used for bicgstab / ca_bicgstab / pipe_bicgstab when the SpMV plan is thread-per-row (LANES = 1); everything else
-// (and pipe_bicgstab_rr) stays on the multi-kernel path of solve.cu.  BICG_MEGA=0 disables it.
+// Synchronisation (the replacement of MPI_Iallreduce/MPI_Wait and of the grid barriers of round 1):
+//   arrive   : a CTA publishes its partial dots as self-validating LL words {generation | 32 data bits} in its own
+//              128-byte slot of the generation's ring entry -- one release fence + plain stores, no atomics;
+//   reduce   : (1 GPU) every CTA polls all slots of the generation (160 threads, one slot each) and adds them in a
+//              fixed order; (N GPUs) only CTA 0 does that, posts the rank's sums into every rank's mailbox over
+//              NVLink (LL words again), and every CTA of every rank polls its own GPU's 8 mailboxes and adds them in
+//              rank order.  Critical path: one L2 round trip (+ one NVLink hop + one L2 round trip);
+//   post / complete : the same, split (MPI_Iallreduce ... SpMV ... MPI_Wait of the pipelined variants);
+//   neighbour wait  : where solver.c has no reduction but the next SpMV gathers what other CTAs just wrote (q, p,
+//              s, ...), a CTA waits only for the CTAs that own the columns its rows reference (a handful for banded
+//              matrices) and -- if its rows reference ghost columns -- for the halo flags of the peers' CTAs that
+//              push them (one flag per pushing CTA, written after that CTA's own system-scope fence).
+// Coherence: gathered vectors are read with plain (L1-cached) loads; every wait ends in an acquire fence at gpu /
+// system scope (SASS: CCTL.IVALL), so lines rewritten by other SMs / peers are re-fetched from L2.
+// Every wait is bounded by PEER_TIMEOUT_NS: a lost CTA or rank raises Scalars::error instead of hanging the GPU.
 #include "mega.cuh"
 #include "vec_body.cuh"
 
@@ -26,20 +35,35 @@ namespace bicg {
 namespace {
 
 constexpr int PROW_PAD = 8;
+constexpr int RED_THREADS = MEGA_MAX_CTAS;          // one polled slot per thread
+constexpr int RED_WARPS = RED_THREADS / 32;
 struct StageHdr { int row0, row1; unsigned a0; int rowa; };
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void cbar(int nthreads)          // consumer-only CTA barrier (the producer warp free-runs)
+__device__ __forceinline__ void nbar(int id, int nthreads)  // named CTA barrier (the producer warp free-runs)
 {
-    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ double ld_coherent(const double *p)    // plain ld.global: L1-cached, never the .nc path
+__device__ __forceinline__ unsigned long long l2_evict_first_policy()
 {
-    double v;
-    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(unsigned dst_smem, const void *src, unsigned bytes, unsigned bar,
+                                                 unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+template <int LANES>
+__device__ __forceinline__ double lanes_sum(double v)
+{
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
@@ -51,12 +75,12 @@ __device__ __forceinline__ void cblock_sum(double (&v)[N], double *scratch)
     constexpr int NW = CT / 32;
 #pragma unroll
     for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
-    cbar(CT);
+    nbar(1, CT);
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < N; ++k) scratch[warp * N + k] = v[k];
     }
-    cbar(CT);
+    nbar(1, CT);
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
@@ -68,99 +92,277 @@ __device__ __forceinline__ void cblock_sum(double (&v)[N], double *scratch)
 
 enum Epi : int { EPI_NONE = 0, EPI_RH_Y, EPI_QY_YY, EPI_CA4 };
 
-template <int CT>
+struct MegaShared {
+    Scalars sc;                               // this CTA's copy of the solver scalars
+    double tot[MAIL_VALS];                    // reduced values of the current synchronisation point
+    double red[RED_WARPS][MAIL_VALS];
+    double contrib[MAX_RANKS][MAIL_VALS];
+    double scratch[32 * MAX_DOTS];
+    unsigned long long full_bar[4], empty_bar[4];
+    StageHdr hdr[4];
+    volatile int flags[4];                    // [1] producer stop, [2] consumed visits, [3] a wait timed out
+};
+
+template <int CT, int LANES>
 struct Mega {
-    static constexpr int RPT = CT, PROW = RPT + PROW_PAD, NCW = CT / 32, UNR = 16;
+    static constexpr int RPT = CT / LANES, PROW = RPT + PROW_PAD, NCW = CT / 32, UNR = (LANES == 1) ? 16 : 8;
+    static_assert(CT >= RED_THREADS, "the slot reduction uses one thread per CTA slot");
 
     const MegaArgs &a;
+    MegaShared &sh;
     unsigned char *dyn;
-    unsigned long long *full_bar, *empty_bar;
-    StageHdr *hdr;
-    double *scratch;
-    volatile int *s_flags;        // [0] master, [1] stop, [2] consumed visits
-    int tid, t0, my_tiles, row_lo, row_hi;
+    int tid, lane, my_tiles, row_lo, row_hi;
     unsigned vis;                 // SpMV tile visits consumed so far (mirrors the producer's counter)
-    unsigned my_gen;              // grid-barrier generation (same value in every CTA)
+    unsigned gen;                 // arrival generation (same value in every CTA)
+    unsigned red_epoch;           // cross-GPU reductions posted (same value on every rank)
+    unsigned posted_gen;          // generation of the reduction posted and not yet completed
+    unsigned long long halo_epoch;
+    int dep_lo, dep_hi;           // CTAs owning the own columns this CTA's rows reference
+    unsigned need_senders;        // ranks whose halo pushes this CTA's rows reference
+    unsigned push_slots;          // push slots (peers) that need rows of this CTA
     size_t stage_bytes;
-    bool failed;
+    int trace_it, trace_who;
 
-    __device__ Mega(const MegaArgs &args) : a(args) {}
+    __device__ Mega(const MegaArgs &args, MegaShared &s) : a(args), sh(s) {}
 
-    // ---------------------------------------------------------------- grid barrier + master work ----------
-    template <int NDOT>
-    __device__ void barrier(double (&dot)[NDOT > 0 ? NDOT : 1], TailDesc td, bool pushed = false)
+    __device__ bool stop_now() const { return sh.sc.done != 0 || sh.sc.error != 0; }
+    __device__ void fail() { sh.flags[3] = 1; }
+    __device__ void mark(int slot)
     {
-        if (NDOT > 0) cblock_sum<(NDOT > 0 ? NDOT : 1), CT>(dot, scratch);
-        cbar(CT);                                     // every consumer's stores happen-before thread 0's fence
-        const unsigned gen = my_gen;                  // generation this barrier closes; every CTA counts them locally
-        if (tid == 0) {
-#pragma unroll
-            for (int k = 0; k < NDOT; ++k) __stcg(&a.partials[(size_t)blockIdx.x * MAX_DOTS + k], dot[k]);
-            // release: the CTA barrier above + this fence order every store of the CTA (at system scope when this
-            // CTA's rows went to peers) before the arrival
-            if (pushed) __threadfence_system(); else __threadfence();
-            const unsigned prev = atomicAdd(&a.bar->count, 1u);
-            s_flags[0] = (prev == gridDim.x - 1);
-        }
-        cbar(CT);
-        if (s_flags[0]) {
-            // last arriver = master: everyone else of the grid is parked, so its extra work delays nobody twice
-            if (tid < 32) {
-                __threadfence();
-                double tot[NDOT > 0 ? NDOT : 1];
-#pragma unroll
-                for (int k = 0; k < (NDOT > 0 ? NDOT : 1); ++k) tot[k] = 0.0;
-                if (NDOT > 0) {
-                    for (unsigned b = tid; b < gridDim.x; b += 32) {
-#pragma unroll
-                        for (int k = 0; k < NDOT; ++k) tot[k] += __ldcg(&a.partials[(size_t)b * MAX_DOTS + k]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < NDOT; ++k) tot[k] = warp_sum(tot[k]);
-                }
-                KernelCommon kc;
-                kc.sc = a.sc; kc.partials = a.partials; kc.hist = a.hist; kc.comm = a.comm; kc.tail = td;
-                tail_warp<NDOT>(kc, tot, true);
-                if (tid == 0) {
-                    a.bar->count = 0u;
-                    st_release_gpu(&a.bar->gen, gen + 1u);      // release: orders the scalars and the counter reset
-                }
-            }
-        } else if (tid == 0) {
-            const unsigned long long t_start = globaltimer_ns();
-            unsigned spins = 0;
-            while (ld_acquire_gpu(&a.bar->gen) == gen) {        // acquire: later loads of this SM see the released data
-                __nanosleep(32);
-                if ((++spins & 1023u) == 0 && globaltimer_ns() - t_start > 2 * PEER_TIMEOUT_NS) { a.sc->error = 1; break; }
-            }
-        }
-        my_gen = gen + 1u;
-        cbar(CT);
+        if (a.trace && trace_who >= 0 && tid == 0 && trace_it < MEGA_TRACE_ITERS)
+            a.trace[((size_t)trace_who * MEGA_TRACE_ITERS + trace_it) * MEGA_TRACE_SLOTS + slot] = globaltimer_ns();
     }
+
+    // ---------------------------------------------------------------- arrive ------------------------------
+    // Publish NV partial sums (NV = 0: presence only) for generation ++gen.  halo: this synchronisation point also
+    // carries a halo exchange -- CTAs that pushed rows to peers fence at system scope and raise their flag there.
+    template <int NV>
+    __device__ void arrive(double (&dot)[NV > 0 ? NV : 1], bool halo)
+    {
+        // a CTA barrier (inside cblock_sum, or the explicit one) puts every consumer's stores of the phase before the fence
+        if (NV > 0) cblock_sum<(NV > 0 ? NV : 1), CT>(dot, sh.scratch);
+        else nbar(1, CT);
+        ++gen;
+        if (halo) ++halo_epoch;
+        const bool pushed = halo && push_slots != 0u;
+        if (tid < 32) {
+            // release: the CTA barrier above + this fence order every store of the CTA (at system scope when its
+            // rows went to peers) before the words below
+            if (pushed) fence_sys(); else fence_gpu();
+            MegaSlot *s = &a.sync->slot[gen & (MEGA_RING - 1)][blockIdx.x];
+            constexpr int NW = NV > 0 ? 2 * NV : 1;
+            if (lane < NW) {
+                unsigned data = 0u;
+                if (NV > 0) {
+                    double v = dot[0];
+#pragma unroll
+                    for (int k = 1; k < NV; ++k) v = ((lane >> 1) == k) ? dot[k] : v;
+                    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+                    data = (lane & 1) ? (unsigned)(b >> 32) : (unsigned)b;
+                }
+                st_ll_gpu(&s->w[lane], ll_pack(data, gen));
+            }
+            if (pushed) {
+#pragma unroll
+                for (int s2 = 0; s2 < MAX_RANKS - 1; ++s2)
+                    if (lane == s2 && ((push_slots >> s2) & 1u)) st_flag_sys(a.push.hflag_dst[s2] + blockIdx.x, halo_epoch);
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- neighbour wait ----------------------
+    __device__ void wait_nbr(bool halo)
+    {
+        if (tid < 32) {
+            bool ok = true;
+            const unsigned long long t0 = globaltimer_ns();
+            const MegaSlot *ring = a.sync->slot[gen & (MEGA_RING - 1)];
+            for (int c = dep_lo + lane; c <= dep_hi; c += 32) {
+                if (c == (int)blockIdx.x) continue;
+                unsigned spins = 0;
+                while ((unsigned)(ld_ll_gpu(&ring[c].w[0]) >> 32) != gen)
+                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
+            }
+            const bool remote = halo && need_senders != 0u;
+            if (remote) {
+                for (int s = 0; s < a.comm.world; ++s) {
+                    if (!((need_senders >> s) & 1u)) continue;
+                    const unsigned long long *f = a.sync->hflag[s];
+                    for (int i = lane; i < MEGA_MAX_CTAS; i += 32) {
+                        if (!((a.sync->pusher_mask[s][i >> 5] >> (i & 31)) & 1u)) continue;
+                        unsigned spins = 0;
+                        while (ld_relaxed_sys(&f[i]) < halo_epoch)
+                            if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
+                    }
+                }
+            }
+            if (remote) fence_sys(); else fence_gpu();       // acquire (+ L1 invalidate): the gathers that follow see the data
+            if (!__all_sync(0xffffffffu, ok) && lane == 0) fail();
+        }
+        nbar(1, CT);
+        if (sh.flags[3]) { if (tid == 0) { sh.sc.error = 1; sh.sc.done = 1; } nbar(1, CT); }
+    }
+    __device__ void sync_nbr(bool halo)
+    {
+        double d0[1] = {0.0};
+        halo = halo && a.comm.world > 1;
+        arrive<0>(d0, halo);
+        wait_nbr(halo);
+    }
+
+    // ---------------------------------------------------------------- reductions --------------------------
+    // All slots of generation g -> sh.tot (fixed order: thread c takes CTA c, butterfly inside each of the five
+    // warps, then warp 0..4 left to right).  Called by every consumer thread; sh.tot is valid for tid 0 on return.
+    template <int NV>
+    __device__ void local_reduce(unsigned g)
+    {
+        if (tid < RED_THREADS) {
+            double v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = 0.0;
+            if (tid < (int)gridDim.x) {
+                const unsigned long long *w = a.sync->slot[g & (MEGA_RING - 1)][tid].w;
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned long long w0[NV], w1[NV];
+                unsigned spins = 0;
+                for (;;) {
+                    bool all = true;
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) { ld_ll_gpu2(w + 2 * k, w0[k], w1[k]); all = all && ll_valid(w0[k], w1[k], g); }
+                    if (all) break;
+                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { fail(); break; }
+                }
+#pragma unroll
+                for (int k = 0; k < NV; ++k) v[k] = ll_decode(w0[k], w1[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) sh.red[tid >> 5][k] = v[k];
+            }
+            nbar(2, RED_THREADS);
+            if (tid == 0) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    double t = sh.red[0][k];
+#pragma unroll
+                    for (int wq = 1; wq < RED_WARPS; ++wq) t += sh.red[wq][k];
+                    sh.tot[k] = t;
+                }
+            }
+        }
+    }
+    // warp 0 of CTA 0: this rank's sums -> every rank's mailbox[parity][me]
+    template <int NV>
+    __device__ void post_mail()
+    {
+        __syncwarp();
+        if (lane < a.comm.world) {
+            MegaSlot *mb = a.peer_mail[0];
+#pragma unroll
+            for (int p = 1; p < MAX_RANKS; ++p) mb = (lane == p) ? a.peer_mail[p] : mb;
+            mb += (size_t)(red_epoch & 1u) * MAX_RANKS + a.comm.rank;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                unsigned long long w0, w1;
+                ll_encode(sh.tot[k], red_epoch, w0, w1);
+                st_ll_sys(&mb->w[2 * k], w0, w1);
+            }
+        }
+        __syncwarp();
+    }
+    // warp 0 of every CTA: the ranks' sums from this GPU's own mailboxes, added in rank order -> sh.tot
+    template <int NV>
+    __device__ void mail_reduce()
+    {
+        if (lane < a.comm.world) {
+            const unsigned long long *w = a.sync->mail[red_epoch & 1u][lane].w;
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned long long w0[NV], w1[NV];
+            unsigned spins = 0;
+            for (;;) {
+                bool all = true;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) { ld_ll_sys(w + 2 * k, w0[k], w1[k]); all = all && ll_valid(w0[k], w1[k], red_epoch); }
+                if (all) break;
+                if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { fail(); break; }
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) sh.contrib[lane][k] = ll_decode(w0[k], w1[k]);
+        }
+        __syncwarp();
+        if (lane < NV) {
+            double acc = sh.contrib[0][lane];
+            for (int p = 1; p < a.comm.world; ++p) acc += sh.contrib[p][lane];
+            sh.tot[lane] = acc;
+        }
+        __syncwarp();
+    }
+    // complete the reduction published at generation g and evaluate the scalar recurrence `fin` in this CTA's copy
+    template <int NV>
+    __device__ void finish(unsigned g, int fin, bool posted)
+    {
+        if (a.comm.world == 1) local_reduce<NV>(g);
+        else {
+            if (blockIdx.x == 0 && !posted) { local_reduce<NV>(g); if (tid < 32) post_mail<NV>(); }
+            if (tid < 32) mail_reduce<NV>();
+        }
+        if (tid == 0) {
+            fence_gpu();
+            if (sh.flags[3]) { sh.sc.error = 1; sh.sc.done = 1; }
+            else finalize(fin, &sh.sc, blockIdx.x == 0 ? a.hist : nullptr, sh.tot);
+        }
+        nbar(1, CT);
+    }
+    template <int NV>
+    __device__ void reduce(double (&dot)[NV], int fin)          // blocking sync point (MPI_Iallreduce + MPI_Wait)
+    {
+        arrive<NV>(dot, false);
+        if (a.comm.world > 1) ++red_epoch;
+        finish<NV>(gen, fin, false);
+    }
+    template <int NV>
+    __device__ void post(double (&dot)[NV], bool halo)          // MPI_Iallreduce (+ the halo of the SpMV that hides it)
+    {
+        halo = halo && a.comm.world > 1;
+        arrive<NV>(dot, halo);
+        posted_gen = gen;
+        if (a.comm.world > 1) {
+            ++red_epoch;
+            if (blockIdx.x == 0) { local_reduce<NV>(gen); if (tid < 32) post_mail<NV>(); }
+        }
+        wait_nbr(halo);
+    }
+    template <int NV>
+    __device__ void complete(int fin) { finish<NV>(posted_gen, fin, true); }      // MPI_Wait
 
     // ---------------------------------------------------------------- SpMV over this CTA's tiles ----------
     template <int EPI>
     __device__ void spmv(const double *x, double *y, double (&dot)[4])
     {
         const int stages = a.stages, cap = a.cap;
+        const int sub = tid % LANES, row_in_tile = tid / LANES;
         for (int lt = 0; lt < my_tiles; ++lt, ++vis) {
             const int s = (int)(vis % (unsigned)stages);
-            mbar_wait(smem_u32(&full_bar[s]), (vis / (unsigned)stages) & 1u);
+            mbar_wait(smem_u32(&sh.full_bar[s]), (vis / (unsigned)stages) & 1u);
             const unsigned char *st = dyn + (size_t)s * stage_bytes;
             const double   *sval = reinterpret_cast<const double *>(st);
             const unsigned *scol = reinterpret_cast<const unsigned *>(sval + cap);
             const unsigned *sptr = scol + cap;
-            const StageHdr h = hdr[s];
-            const int row = h.row0 + tid;
+            const StageHdr h = sh.hdr[s];
+            const int row = h.row0 + row_in_tile;
             const bool valid = row < h.row1;
             int j = 0, e = 0;
             double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;     // epilogue operands: in flight during the gathers
             if (valid) {
-                j = (int)(sptr[row - h.rowa] - h.a0);
+                j = (int)(sptr[row - h.rowa] - h.a0) + sub;
                 e = (int)(sptr[row - h.rowa + 1] - h.a0);
-                if (EPI == EPI_RH_Y) e0 = a.v.rh[row];
-                if (EPI == EPI_QY_YY) e0 = a.v.r[row];
-                if (EPI == EPI_CA4) { e0 = a.v.rh[row]; e1 = a.v.r[row]; e2 = a.v.s[row]; e3 = a.v.z[row]; }
+                if (sub == 0) {
+                    if (EPI == EPI_RH_Y) e0 = a.v.rh[row];
+                    if (EPI == EPI_QY_YY) e0 = a.v.r[row];
+                    if (EPI == EPI_CA4) { e0 = a.v.rh[row]; e1 = a.v.r[row]; e2 = a.v.s[row]; e3 = a.v.z[row]; }
+                }
             }
             double acc = 0.0;
             while (j < e) {
@@ -168,7 +370,7 @@ struct Mega {
                 double v[UNR], xv[UNR];
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) {
-                    const int idx = min(j + u, e - 1);
+                    const int idx = min(j + u * LANES, e - 1);
                     c[u] = scol[idx];
                     v[u] = sval[idx];
                 }
@@ -176,10 +378,11 @@ struct Mega {
                 for (int u = 0; u < UNR; ++u) xv[u] = ld_coherent(x + c[u]);
 #pragma unroll
                 for (int u = 0; u < UNR; ++u)
-                    if (j + u < e) acc = fma(v[u], xv[u], acc);
-                j += UNR;
+                    if (j + u * LANES < e) acc = fma(v[u], xv[u], acc);
+                j += UNR * LANES;
             }
-            if (valid) {
+            acc = lanes_sum<LANES>(acc);
+            if (valid && sub == 0) {
                 y[row] = acc;
                 if (EPI == EPI_RH_Y) dot[0] = fma(e0, acc, dot[0]);
                 if (EPI == EPI_QY_YY) { dot[0] = fma(e0, acc, dot[0]); dot[1] = fma(acc, acc, dot[1]); }
@@ -189,226 +392,175 @@ struct Mega {
                 }
             }
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+            if (lane == 0) mbar_arrive(smem_u32(&sh.empty_bar[s]));
         }
     }
 
     // ---------------------------------------------------------------- vector phase over the CTA's own rows --
+    // row_lo is a multiple of 16 and every arena vector is 128-byte aligned: 16-byte accesses, two in flight per
+    // vector and thread
     template <int PH>
     __device__ void vec(double *dot)
     {
         Coef c;
-        c.al = __ldcg(&a.sc->alpha); c.be = __ldcg(&a.sc->beta); c.om = __ldcg(&a.sc->omega);
+        c.al = sh.sc.alpha; c.be = sh.sc.beta; c.om = sh.sc.omega;
         c.nbo = -c.be * c.om;
-        int i = row_lo + tid;
-        for (; i + 3 * CT < row_hi; i += 4 * CT) body<PH, Strided<4, CT>>(a.v, i, c, dot);
-        for (; i + CT < row_hi; i += 2 * CT) body<PH, Strided<2, CT>>(a.v, i, c, dot);
-        for (; i < row_hi; i += CT) body<PH, Strided<1, CT>>(a.v, i, c, dot);
+        const int hi2 = row_lo + ((row_hi - row_lo) & ~1);
+        int i = row_lo + 2 * tid;
+        for (; i + 2 * CT < hi2; i += 4 * CT) body<PH, Pairs<2, 2 * CT>>(a.v, i, c, dot);
+        for (; i < hi2; i += 2 * CT) body<PH, Pairs<1, 2 * CT>>(a.v, i, c, dot);
+        if (tid == 0 && hi2 < row_hi) body<PH, Contig<1>>(a.v, hi2, c, dot);
     }
-    __device__ bool push(const PushDesc &pd)          // true: this CTA stored to a peer
+    // copy the rows of vector `id` that peers gather into their ghost regions (NVLink stores); the flag follows in arrive()
+    __device__ void push(int id)
     {
-        if (pd.npeers == 0 || !push_touches(pd, row_lo, row_hi)) return false;
-        cbar(CT);                                     // the rows being pushed are final
+        if (a.comm.world == 1 || push_slots == 0u) return;
+        nbar(1, CT);                                  // the rows being pushed are final
+        PushDesc pd;
+        pd.npeers = a.push.npeers; pd.fence_writers = 0;
+        pd.src = a.vec_base + (long long)id * a.vstride;
+#pragma unroll
+        for (int s = 0; s < MAX_RANKS - 1; ++s) {
+            pd.dst[s] = a.push.ghost0[s] + (long long)id * a.push.vstride[s];
+            pd.runs[s] = a.push.runs[s];
+            pd.nruns[s] = ((push_slots >> s) & 1u) ? a.push.nruns[s] : 0;
+        }
         push_chunk(pd, row_lo, row_hi, tid, CT);
-        return true;
     }
-    int trace_it = 0;
-    __device__ void mark(int slot)
-    {
-        if (a.trace && blockIdx.x == 0 && tid == 0 && trace_it < MEGA_TRACE_ITERS)
-            a.trace[trace_it * MEGA_TRACE_SLOTS + slot] = globaltimer_ns();
-    }
-    __device__ bool stop_now() { return __ldcg(&a.sc->done) != 0 || __ldcg(&a.sc->error) != 0; }
-
-    static __device__ TailDesc td_red(int fin, int ndot, int npend = 0) { return TailDesc{TAIL_ALLREDUCE, fin, ndot, npend, 0, 0, 0}; }
-    static __device__ TailDesc td_post(int ndot) { return TailDesc{TAIL_POST, FIN_NONE, ndot, 0, 0, 0, 0}; }
-    static __device__ TailDesc td_complete(int fin, int nred) { return TailDesc{TAIL_COMPLETE, fin, 0, 0, 0, nred, 0}; }
-    static __device__ TailDesc td_pend(int ndot) { return TailDesc{TAIL_PEND, FIN_NONE, ndot, 0, 0, 0, 0}; }
-    __device__ TailDesc with_halo(TailDesc t) const { t.signal_halo = a.comm.world > 1 ? 1 : 0; return t; }
-    static __device__ TailDesc td_none() { return TailDesc{TAIL_NONE, FIN_NONE, 0, 0, 0, 0, 0}; }
 
     // ---------------------------------------------------------------- solver.c:86-127 -----------------------
     __device__ void run_bicgstab()
     {
-        double d4[4], d2[2], d0[1];
-        if (stop_now()) return;                                             // solver.c:86 before the first pass
+        double d4[4], d2[2], d1[1], d0[1];
+        d0[0] = 0.0;
         while (true) {
             mark(0);
             d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
             spmv<EPI_RH_Y>(a.v.p, a.v.s, d4);                               // s = A p, (r#,s)           :88-91
             mark(1);
-            { double t1[1] = {d4[0]}; barrier<1>(t1, td_red(FIN_BICG_ALPHA, 1)); }
+            d1[0] = d4[0];
+            reduce<1>(d1, FIN_BICG_ALPHA);                                  // alpha                      :93
             mark(2);
             if (stop_now()) break;
             vec<PH_BICG_Q>(d0);                                             // q = r - alpha s            :94
-            const bool pr = push(a.push_r);
+            push(V_R);
             mark(3);
-            barrier<0>(d0, with_halo(td_none()), pr);
+            sync_nbr(true);
             mark(4);
             d4[0] = d4[1] = 0.0;
             spmv<EPI_QY_YY>(a.v.r, a.v.y, d4);                              // y = A q, (q,y), (y,y)      :96-102
             mark(5);
             d2[0] = d4[0]; d2[1] = d4[1];
-            barrier<2>(d2, td_red(FIN_BICG_OMEGA, 2));
+            reduce<2>(d2, FIN_BICG_OMEGA);                                  // omega                      :104
             mark(6);
             d2[0] = d2[1] = 0.0;
             vec<PH_BICG_XR>(d2);                                            // x, r, (r,r), (r#,r)        :105-114
             mark(7);
-            barrier<2>(d2, td_red(FIN_BICG_BETA, 2));                       // beta, k++, loop test       :116-120
+            reduce<2>(d2, FIN_BICG_BETA);                                   // beta, k++, loop test       :116-120
             mark(8);
             if (stop_now()) break;
             vec<PH_BICG_P>(d0);                                             // p                          :117-119
-            const bool pp = push(a.push_p);
+            push(V_P);
             mark(9);
-            barrier<0>(d0, with_halo(td_none()), pp);
+            sync_nbr(true);
             mark(10);
             ++trace_it;
-        }
-    }
-    // EXPERIMENTAL (BICG_MEGA_FUSEQ=1, off by default; parity-green on one GPU, not yet timed, not yet run multi-GPU): y = A q with
-    // q[col] = r[col] - alpha s[col] gathered on the fly (solver.c:94 folded into :96), q[row] written to the spare
-    // vector ax, dots (q,y), (y,y).  Removes the q vector phase and one grid barrier per iteration.
-    __device__ void spmv_fq(double alpha, double (&dot)[4])
-    {
-        constexpr int UQ = 8;
-        const int stages = a.stages, cap = a.cap;
-        const double *rv = a.v.r, *sv = a.v.s;
-        for (int lt = 0; lt < my_tiles; ++lt, ++vis) {
-            const int s = (int)(vis % (unsigned)stages);
-            mbar_wait(smem_u32(&full_bar[s]), (vis / (unsigned)stages) & 1u);
-            const unsigned char *st = dyn + (size_t)s * stage_bytes;
-            const double   *sval = reinterpret_cast<const double *>(st);
-            const unsigned *scol = reinterpret_cast<const unsigned *>(sval + cap);
-            const unsigned *sptr = scol + cap;
-            const StageHdr h = hdr[s];
-            const int row = h.row0 + tid;
-            const bool valid = row < h.row1;
-            int j = 0, e = 0;
-            double r_row = 0.0, s_row = 0.0;
-            if (valid) {
-                j = (int)(sptr[row - h.rowa] - h.a0);
-                e = (int)(sptr[row - h.rowa + 1] - h.a0);
-                r_row = rv[row]; s_row = sv[row];
-            }
-            double acc = 0.0;
-            while (j < e) {
-                unsigned c[UQ];
-                double v[UQ], xr[UQ], xs[UQ];
-#pragma unroll
-                for (int u = 0; u < UQ; ++u) {
-                    const int idx = min(j + u, e - 1);
-                    c[u] = scol[idx];
-                    v[u] = sval[idx];
-                }
-#pragma unroll
-                for (int u = 0; u < UQ; ++u) { xr[u] = ld_coherent(rv + c[u]); xs[u] = ld_coherent(sv + c[u]); }
-#pragma unroll
-                for (int u = 0; u < UQ; ++u)
-                    if (j + u < e) acc = fma(v[u], fma(-alpha, xs[u], xr[u]), acc);
-                j += UQ;
-            }
-            if (valid) {
-                const double q_row = fma(-alpha, s_row, r_row);
-                a.v.y[row] = acc;
-                a.v.ax[row] = q_row;
-                dot[0] = fma(q_row, acc, dot[0]);
-                dot[1] = fma(acc, acc, dot[1]);
-            }
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[s]));
-        }
-    }
-    __device__ void run_bicgstab_fq()
-    {
-        double d4[4], d2[2], d0[1];
-        if (stop_now()) return;
-        while (true) {
-            d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
-            spmv<EPI_RH_Y>(a.v.p, a.v.s, d4);                               // s = A p, (r#,s)
-            const bool ps = push(a.push_s);                                 // neighbours gather s in the next SpMV
-            { double t1[1] = {d4[0]}; barrier<1>(t1, with_halo(td_red(FIN_BICG_ALPHA, 1)), ps); }
-            if (stop_now()) break;
-            d4[0] = d4[1] = 0.0;
-            spmv_fq(__ldcg(&a.sc->alpha), d4);                              // y = A (r - alpha s), q -> ax
-            d2[0] = d4[0]; d2[1] = d4[1];
-            barrier<2>(d2, td_red(FIN_BICG_OMEGA, 2));
-            d2[0] = d2[1] = 0.0;
-            vec<PH_BICG_XR_Q>(d2);                                          // x, r = q - omega y, (r,r), (r#,r)
-            const bool pr = push(a.push_r);
-            barrier<2>(d2, with_halo(td_red(FIN_BICG_BETA, 2)), pr);
-            if (stop_now()) break;
-            vec<PH_BICG_P>(d0);                                             // p
-            const bool pp = push(a.push_p);
-            barrier<0>(d0, with_halo(td_none()), pp);
         }
     }
     // ---------------------------------------------------------------- solver.c:216-259 ----------------------
     __device__ void run_ca()
     {
-        double d4[4], d2[2], d1[1], d0[1];
-        if (stop_now()) return;
+        double d5[5], d4[4], d2[2], d1[1], d0[1];
+        d0[0] = 0.0;
         while (true) {
             vec<PH_CA_PS>(d0);                                              // p, s                       :217-222
-            const bool ps = push(a.push_s);
-            barrier<0>(d0, with_halo(td_none()), ps);
+            push(V_S);
+            sync_nbr(true);
             d4[0] = 0.0;
             spmv<EPI_NONE>(a.v.s, a.v.z, d4);                               // z = A s                    :224
-            cbar(CT);                                                       // own rows of z written by other warps
+            nbar(1, CT);                                                    // own rows of z written by other warps
             d2[0] = d2[1] = 0.0;
             vec<PH_QY>(d2);                                                 // q, y, (q,y), (y,y)         :225-230
-            barrier<2>(d2, td_red(FIN_OMEGA2, 2));
+            reduce<2>(d2, FIN_OMEGA2);                                      // omega                      :232
+            if (stop_now()) break;
             d1[0] = 0.0;
             vec<PH_CA_XR>(d1);                                              // x, r, local (r,r)          :233-236
-            const bool pr = push(a.push_r);
-            barrier<1>(d1, with_halo(td_pend(1)), pr);
+            push(V_R);
+            sync_nbr(true);
             d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
             spmv<EPI_CA4>(a.v.r, a.v.w, d4);                                // w = A r, 4 dots            :238-247
-            barrier<4>(d4, td_red(FIN_CAPIPE_END, 4, 1));                   // beta, alpha, k++, test     :248-253
+            d5[0] = d4[0]; d5[1] = d4[1]; d5[2] = d4[2]; d5[3] = d4[3]; d5[4] = d1[0];
+            reduce<5>(d5, FIN_CAPIPE_END);                                  // beta, alpha, k++, test     :248-253
             if (stop_now()) break;
         }
     }
-    // ---------------------------------------------------------------- solver.c:351-398 ----------------------
-    __device__ void run_pipe()
+    // ---------------------------------------------------------------- solver.c:351-398 / 494-547 ------------
+    __device__ void run_pipe(bool rr)
     {
         double d5[5], d4[4], d2[2], d0[1];
-        if (stop_now()) return;
+        d0[0] = 0.0; d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
         while (true) {
+            const int k = sh.sc.k;
+            const bool replace = rr && (k % a.krr == 0) && k > 0 && k <= a.krr * a.nrr;   // solver.c:498, 522
             d2[0] = d2[1] = 0.0;
-            vec<PH_PIPE_1>(d2);                                             // p,s,z,q,y + (q,y),(y,y)    :352-364
-            const bool pz = push(a.push_z);
-            barrier<2>(d2, with_halo(td_post(2)), pz);                          // MPI_Iallreduce x2
-            d4[0] = 0.0;
-            spmv<EPI_NONE>(a.v.z, a.v.v, d4);                               // v = A z                    :365
-            barrier<0>(d0, td_complete(FIN_OMEGA2, 2));                     // MPI_Wait x2 -> omega       :366-369
+            if (!replace) {
+                vec<PH_PIPE_1>(d2);                                         // p,s,z,q,y + (q,y),(y,y)    :352-364
+            } else {
+                vec<PH_RR_P>(d0);                                           // p                          :494-496
+                push(V_P);
+                sync_nbr(true);
+                spmv<EPI_NONE>(a.v.p, a.v.s, d4);                           // s = A p                    :499
+                push(V_S);
+                sync_nbr(true);
+                spmv<EPI_NONE>(a.v.s, a.v.z, d4);                           // z = A s                    :500
+                nbar(1, CT);
+                vec<PH_QY>(d2);                                             // q, y, (q,y), (y,y)         :509-512
+            }
+            push(V_Z);
+            post<2>(d2, true);                                              // MPI_Iallreduce x2
+            spmv<EPI_NONE>(a.v.z, a.v.v, d4);                               // v = A z hides it           :365 / 513
+            complete<2>(FIN_OMEGA2);                                        // MPI_Wait x2 -> omega       :366-369
+            if (stop_now()) break;
             d5[0] = d5[1] = d5[2] = d5[3] = d5[4] = 0.0;
-            vec<PH_PIPE_3>(d5);                                             // x, r, w + 5 dots           :370-380
-            const bool pw = push(a.push_w);
-            barrier<5>(d5, with_halo(td_post(5)), pw);
-            spmv<EPI_NONE>(a.v.w, a.v.t, d4);                               // t = A w                    :381
-            barrier<0>(d0, td_complete(FIN_CAPIPE_END, 5));                 // MPI_Wait x5 -> beta, alpha :382-388
+            if (!replace) {
+                vec<PH_PIPE_3>(d5);                                         // x, r, w + 5 dots           :370-380
+            } else {
+                vec<PH_RR_X>(d0);                                           // x                          :518-519
+                push(V_X);
+                sync_nbr(true);
+                spmv<EPI_NONE>(a.v.x, a.v.ax, d4);                          // Ax = A x                   :523
+                nbar(1, CT);
+                vec<PH_RR_R>(d0);                                           // r = b - Ax                 :524-525
+                push(V_R);
+                sync_nbr(true);
+                spmv<EPI_NONE>(a.v.r, a.v.w, d4);                           // w = A r                    :526
+                nbar(1, CT);
+                vec<PH_RR_DOTS>(d5);                                        // 5 dots                     :533-539
+            }
+            push(V_W);
+            post<5>(d5, true);                                              // MPI_Iallreduce x5
+            spmv<EPI_NONE>(a.v.w, a.v.t, d4);                               // t = A w hides it           :381 / 540
+            complete<5>(FIN_CAPIPE_END);                                    // MPI_Wait x5 -> beta, alpha :382-388
             if (stop_now()) break;
         }
     }
 };
 
-template <int CT, bool FQ>
+template <int CT, int LANES>
 __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_constant__ MegaArgs a)
 {
-    using M = Mega<CT>;
+    using M = Mega<CT, LANES>;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ __align__(8) unsigned long long full_bar[4], empty_bar[4];
-    __shared__ StageHdr hdr[4];
-    __shared__ double scratch[32 * MAX_DOTS];
-    __shared__ int s_flags[4];
+    __shared__ __align__(16) MegaShared sh;
 
     const int tid = threadIdx.x;
     const int stages = a.stages, cap = a.cap;
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(smem_u32(&full_bar[s]), 1u);
-            mbar_init(smem_u32(&empty_bar[s]), (unsigned)M::NCW);
+            mbar_init(smem_u32(&sh.full_bar[s]), 1u);
+            mbar_init(smem_u32(&sh.empty_bar[s]), (unsigned)M::NCW);
         }
-        s_flags[0] = s_flags[1] = s_flags[2] = 0;
+        sh.flags[0] = sh.flags[1] = sh.flags[2] = sh.flags[3] = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -420,14 +572,16 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
     if (tid >= CT) {
         // ============================ producer warp: streams this CTA's tiles round and round ==============
         if (tid == CT && my_tiles > 0) {
-            volatile int *flags = s_flags;
+            volatile int *flags = sh.flags;
+            const unsigned long long pol = l2_evict_first_policy();
+            const bool hint = a.l2_hint != 0;
             unsigned v = 0;
             bool stop = false;
             for (;; ++v) {
                 const int s = (int)(v % (unsigned)stages);
                 if (v >= (unsigned)stages) {
                     const unsigned par = (v / (unsigned)stages - 1u) & 1u;
-                    while (!mbar_try_wait(smem_u32(&empty_bar[s]), par)) {
+                    while (!mbar_try_wait(smem_u32(&sh.empty_bar[s]), par)) {
                         if (flags[1]) { stop = true; break; }
                     }
                 }
@@ -441,73 +595,163 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
                 double   *sval = reinterpret_cast<double *>(st);
                 unsigned *scol = reinterpret_cast<unsigned *>(sval + cap);
                 unsigned *sptr = scol + cap;
-                hdr[s] = StageHdr{row0, row1, a0, rowa};
-                const unsigned bar = smem_u32(&full_bar[s]);
+                sh.hdr[s] = StageHdr{row0, row1, a0, rowa};
+                const unsigned bar = smem_u32(&sh.full_bar[s]);
                 mbar_arrive_expect_tx(bar, cnt * 12u + (unsigned)cntp * 4u);
                 if (cnt) {
-                    tma_load_1d(smem_u32(sval), a.val + a0, cnt * 8u, bar);
-                    tma_load_1d(smem_u32(scol), a.col + a0, cnt * 4u, bar);
+                    if (hint) {
+                        tma_load_1d_hint(smem_u32(sval), a.val + a0, cnt * 8u, bar, pol);
+                        tma_load_1d_hint(smem_u32(scol), a.col + a0, cnt * 4u, bar, pol);
+                    } else {
+                        tma_load_1d(smem_u32(sval), a.val + a0, cnt * 8u, bar);
+                        tma_load_1d(smem_u32(scol), a.col + a0, cnt * 4u, bar);
+                    }
                 }
                 tma_load_1d(smem_u32(sptr), a.ptr + rowa, (unsigned)cntp * 4u, bar);
             }
             // drain: bulk copies already issued must land before the CTA may retire its shared memory
             const unsigned consumed = (unsigned)flags[2];
             for (unsigned w = consumed; w < v; ++w)
-                mbar_wait(smem_u32(&full_bar[w % (unsigned)stages]), (w / (unsigned)stages) & 1u);
+                mbar_wait(smem_u32(&sh.full_bar[w % (unsigned)stages]), (w / (unsigned)stages) & 1u);
         }
     } else {
         // ============================ consumer warps: the solver ============================================
-        M m(a);
-        m.dyn = dyn_smem; m.full_bar = full_bar; m.empty_bar = empty_bar; m.hdr = hdr; m.scratch = scratch;
-        m.s_flags = s_flags; m.tid = tid; m.t0 = t0; m.my_tiles = my_tiles; m.vis = 0u; m.stage_bytes = stage_bytes;
-        m.row_lo = a.tile_row[t0]; m.row_hi = a.tile_row[t1]; m.failed = false;
-        m.my_gen = ld_acquire_gpu(&a.bar->gen);       // left by the previous solve; nobody can have advanced it yet
-        if constexpr (FQ) m.run_bicgstab_fq();
-        else if (a.method == 0) m.run_bicgstab();
-        else if (a.method == 1) m.run_ca();
-        else m.run_pipe();
-        cbar(CT);
-        if (tid == 0) { s_flags[2] = (int)m.vis; __threadfence_block(); s_flags[1] = 1; }
+        M m(a, sh);
+        m.dyn = dyn_smem; m.tid = tid; m.lane = tid & 31; m.my_tiles = my_tiles; m.vis = 0u; m.stage_bytes = stage_bytes;
+        m.row_lo = a.tile_row[t0]; m.row_hi = a.tile_row[t1];
+        m.trace_it = 0;
+        m.trace_who = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 2 ? 1 : -1);
+        // counters left by the previous solve; nobody advances them before every CTA has passed its first arrive
+        m.gen = a.sync->st.gen; m.red_epoch = a.sync->st.red_epoch; m.halo_epoch = a.sync->st.halo_epoch;
+        m.posted_gen = m.gen;
+        if (tid == 0) sh.sc = *a.sc;                  // the scalars the init kernels left (solver.c:74-83, 200-213)
+
+        // which CTAs own the columns my rows gather, which ranks fill the ghost slots they gather
+        const int4 dep = a.cta_dep[blockIdx.x];
+        const int G = (int)gridDim.x;
+        auto cta_of_row = [&](int r) {              // last CTA whose first row is <= r
+            int lo = 0, hi = G;                     // first rows are non-decreasing; a.tile_row[a.cta_tile[G]] = rows
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.tile_row[a.cta_tile[mid]] <= r) lo = mid + 1; else hi = mid; }
+            return lo - 1;
+        };
+        m.dep_lo = 1; m.dep_hi = 0;
+        if (dep.x <= dep.y) { m.dep_lo = max(0, cta_of_row(dep.x)); m.dep_hi = min(G - 1, cta_of_row(dep.y)); }
+        m.need_senders = 0u;
+        if (a.comm.world > 1 && dep.z <= dep.w)
+            for (int p = 0; p < a.comm.world; ++p)
+                if (a.ghost_first[p] <= dep.w && a.ghost_first[p + 1] > dep.z) m.need_senders |= 1u << p;
+        m.push_slots = 0u;
+        if (a.comm.world > 1) {
+            PushDesc pd;
+            pd.npeers = 1;
+            for (int s = 0; s < a.push.npeers; ++s) {
+                pd.runs[0] = a.push.runs[s]; pd.nruns[0] = a.push.nruns[s];
+                if (m.row_hi > m.row_lo && push_touches(pd, m.row_lo, m.row_hi)) m.push_slots |= 1u << s;
+            }
+        }
+        nbar(1, CT);
+        if (a.comm.world > 1 && m.need_senders != 0u) {
+            // the vector the first SpMV gathers was pushed by the init kernels (kernel-per-phase protocol)
+            if (tid < 32 && !halo_wait(a.comm, sh.sc.halo_epoch) && tid == 0) { sh.sc.error = 1; sh.sc.done = 1; }
+            if (tid < 32) fence_sys();
+            nbar(1, CT);
+        }
+        if (!m.stop_now()) {                                             // solver.c:86 before the first pass
+            if (a.method == 0) m.run_bicgstab();
+            else if (a.method == 1) m.run_ca();
+            else m.run_pipe(a.method == 3);
+        }
+        nbar(1, CT);
+        if (tid == 0) {
+            sh.flags[2] = (int)m.vis; __threadfence_block(); sh.flags[1] = 1;
+            if (blockIdx.x == 0) {
+                *a.sc = sh.sc;
+                a.sync->st.gen = m.gen; a.sync->st.red_epoch = m.red_epoch; a.sync->st.halo_epoch = m.halo_epoch;
+            } else if (sh.sc.error) a.sc->error = 1;
+        }
     }
 }
 
-template <int CT, bool FQ>
+// per-CTA column ranges: min / max own column and min / max ghost slot over the CTA's entries
+__global__ void __launch_bounds__(256) mega_dep_kernel(const unsigned *__restrict__ col, const unsigned *__restrict__ ptr,
+                                                       const int *__restrict__ tile_row, const int *__restrict__ cta_tile,
+                                                       int ghost_off, int4 *dep)
+{
+    __shared__ int s[4];
+    if (threadIdx.x == 0) { s[0] = 0x7fffffff; s[1] = -1; s[2] = 0x7fffffff; s[3] = -1; }
+    __syncthreads();
+    const int r0 = tile_row[cta_tile[blockIdx.x]], r1 = tile_row[cta_tile[blockIdx.x + 1]];
+    int omin = 0x7fffffff, omax = -1, gmin = 0x7fffffff, gmax = -1;
+    if (r1 > r0) {
+        const unsigned e0 = ptr[r0], e1 = ptr[r1];
+        for (unsigned j = e0 + threadIdx.x; j < e1; j += blockDim.x) {
+            const int c = (int)col[j];
+            if (c < ghost_off) { omin = min(omin, c); omax = max(omax, c); }
+            else { gmin = min(gmin, c - ghost_off); gmax = max(gmax, c - ghost_off); }
+        }
+    }
+    atomicMin(&s[0], omin); atomicMax(&s[1], omax); atomicMin(&s[2], gmin); atomicMax(&s[3], gmax);
+    __syncthreads();
+    if (threadIdx.x == 0) dep[blockIdx.x] = make_int4(s[0], s[1], s[2], s[3]);
+}
+
+template <int CT, int LANES>
 cudaError_t launch(const MegaArgs &a, int grid, size_t smem, cudaStream_t st)
 {
     void *params[1] = {(void *)&a};
-    return cudaLaunchCooperativeKernel((const void *)bicg_mega_kernel<CT, FQ>, dim3(grid), dim3(CT + 32), params, smem, st);
+    return cudaLaunchCooperativeKernel((const void *)bicg_mega_kernel<CT, LANES>, dim3(grid), dim3(CT + 32), params, smem, st);
 }
-template <int CT, bool FQ>
+template <int CT, int LANES>
 cudaError_t set_attr()
 {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, bicg_mega_kernel<CT, FQ>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, bicg_mega_kernel<CT, LANES>);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(bicg_mega_kernel<CT, FQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(bicg_mega_kernel<CT, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 227 * 1024 - (int)fa.sharedSizeBytes);
 }
 
 } // namespace
 
-size_t mega_smem_bytes(int cap, int stages, int threads) { return (size_t)stages * ((size_t)cap * 12u + (size_t)(threads + PROW_PAD) * 4u); }
+size_t mega_smem_bytes(int cap, int stages, int threads, int lanes)
+{
+    return (size_t)stages * ((size_t)cap * 12u + (size_t)(threads / lanes + PROW_PAD) * 4u);
+}
+
+bool mega_has_variant(int threads, int lanes)
+{
+    if (threads == 256) return lanes == 1;
+    return threads == 512 && (lanes == 1 || lanes == 4 || lanes == 8 || lanes == 32);
+}
 
 int mega_setup_attributes()
 {
     cudaError_t e;
-    if ((e = set_attr<256, false>()) != cudaSuccess) return (int)e;
-    if ((e = set_attr<512, false>()) != cudaSuccess) return (int)e;
-    if ((e = set_attr<256, true>()) != cudaSuccess) return (int)e;
-    if ((e = set_attr<512, true>()) != cudaSuccess) return (int)e;
+    if ((e = set_attr<256, 1>()) != cudaSuccess) return (int)e;
+    if ((e = set_attr<512, 1>()) != cudaSuccess) return (int)e;
+    if ((e = set_attr<512, 4>()) != cudaSuccess) return (int)e;
+    if ((e = set_attr<512, 8>()) != cudaSuccess) return (int)e;
+    if ((e = set_attr<512, 32>()) != cudaSuccess) return (int)e;
     return 0;
 }
 
-int launch_mega(int threads, bool fuse_q, int grid, size_t smem, const MegaArgs &a, cudaStream_t st)
+int launch_mega(int threads, int lanes, int grid, size_t smem, const MegaArgs &a, cudaStream_t st)
 {
-    switch (threads) {
-    case 256: return (int)(fuse_q ? launch<256, true>(a, grid, smem, st) : launch<256, false>(a, grid, smem, st));
-    case 512: return (int)(fuse_q ? launch<512, true>(a, grid, smem, st) : launch<512, false>(a, grid, smem, st));
-    default:  return (int)cudaErrorInvalidValue;
+    if (threads == 256 && lanes == 1) return (int)launch<256, 1>(a, grid, smem, st);
+    if (threads != 512) return (int)cudaErrorInvalidValue;
+    switch (lanes) {
+    case 1:  return (int)launch<512, 1>(a, grid, smem, st);
+    case 4:  return (int)launch<512, 4>(a, grid, smem, st);
+    case 8:  return (int)launch<512, 8>(a, grid, smem, st);
+    case 32: return (int)launch<512, 32>(a, grid, smem, st);
+    default: return (int)cudaErrorInvalidValue;
     }
+}
+
+void launch_mega_dep(const unsigned *col, const unsigned *ptr, const int *tile_row, const int *cta_tile, int grid,
+                     int ghost_off, int4 *dep, cudaStream_t st)
+{
+    mega_dep_kernel<<<grid, 256, 0, st>>>(col, ptr, tile_row, cta_tile, ghost_off, dep);
 }
 
 } // namespace bicg

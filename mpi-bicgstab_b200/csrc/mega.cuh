@@ -1,22 +1,58 @@
-// mega.cuh -- argument block + launch interface of the persistent solver kernel (mega.cu)
+// mega.cuh -- argument block, synchronisation state and launch interface of the persistent solver kernel (mega.cu)
 #pragma once
 #include "dev.cuh"
 #include "vec.cuh"
 
 namespace bicg {
 
-// grid barrier state (HBM, zero-initialised): arrival counter and generation flag on separate lines, so the
-// pollers of `gen` do not slow down the arrivals
-struct alignas(256) GridBar { unsigned count; unsigned pad0_[31]; unsigned gen; unsigned pad1_[31]; };
+constexpr int MEGA_MAX_CTAS   = 160;   // >= SM count (148 on B200); one CTA per SM
+constexpr int MEGA_RING       = 8;     // generations of arrival slots kept (a CTA is never more than 3 ahead of another)
+constexpr int MEGA_SLOT_WORDS = 16;    // 8 doubles as LL words
+constexpr int MEGA_MASK_WORDS = MEGA_MAX_CTAS / 32;
+
+// What a CTA leaves at a synchronisation point: its partial dot products as self-validating LL words
+// {generation | 32 data bits} (dev.cuh).  One 128-byte line per CTA and generation, written once, polled by the CTAs
+// that depend on it -- no atomics, no master, no second "release" flag.
+struct alignas(128) MegaSlot { unsigned long long w[MEGA_SLOT_WORDS]; };
+
+// counters that survive from one solve to the next (same value in every CTA / on every rank)
+struct alignas(128) MegaState {
+    unsigned gen;                       // last arrival generation used
+    unsigned red_epoch;                 // last cross-GPU reduction posted
+    unsigned long long halo_epoch;      // last halo exchange signalled
+    int plan_ok[MAX_RANKS];             // written by rank p at plan time: its persistent-kernel plan is usable
+};
+
+// Lives in the IPC-shared arena: `mail`, `hflag`, `pusher_mask` and `st.plan_ok` are written by the peers.
+struct MegaSync {
+    MegaState st;
+    MegaSlot  slot[MEGA_RING][MEGA_MAX_CTAS];
+    MegaSlot  mail[2][MAX_RANKS];                           // [epoch parity][source rank]: that rank's local sums
+    unsigned long long hflag[MAX_RANKS][MEGA_MAX_CTAS];     // [sender][sender's CTA] = halo epoch that CTA has pushed
+    unsigned pusher_mask[MAX_RANKS][MEGA_MASK_WORDS + 3];   // [sender]: which of its CTAs push to this rank
+};
+
+// where the boundary runs of any arena vector go on the peers (the per-vector PushDesc is derived on the device)
+struct PushPlan {
+    int npeers;
+    int peer[MAX_RANKS - 1];                 // rank of push slot i
+    double *ghost0[MAX_RANKS - 1];           // peer-mapped address of vector 0's ghost region on that rank
+    long long vstride[MAX_RANKS - 1];        // that rank's distance between consecutive vectors (doubles)
+    const PushRun *runs[MAX_RANKS - 1];
+    int nruns[MAX_RANKS - 1];
+    unsigned long long *hflag_dst[MAX_RANKS - 1];   // that rank's sync->hflag[this rank]: one flag per pushing CTA
+};
 
 constexpr int MEGA_TRACE_ITERS = 256, MEGA_TRACE_SLOTS = 16;
 
 struct MegaArgs {
     Scalars *sc;
-    double  *partials;          // [grid][MAX_DOTS]
     double  *hist;
-    CommDev  comm;
-    GridBar *bar;
+    CommDev  comm;              // kernel-per-phase protocol state (only for the halo wait on entry)
+    MegaSync *sync;             // this rank's
+    MegaSlot *peer_mail[MAX_RANKS];              // rank p's sync->mail[0]
+    const int *ghost_first;     // [world + 1]: first ghost slot received from each owner (slots are grouped by owner)
+    const int4 *cta_dep;        // [grid]: min / max own column, min / max ghost slot referenced by the CTA's rows
     const double   *val;
     const unsigned *col;
     const unsigned *ptr;
@@ -24,15 +60,22 @@ struct MegaArgs {
     const unsigned *tile_nz;    // ntiles + 1
     const int      *cta_tile;   // grid + 1 : first tile of every CTA (contiguous ownership)
     int cap, stages;
+    int ghost_off;
+    int l2_hint;                // 1: matrix stream is loaded with an L2 evict-first policy
+    double *vec_base; long long vstride;   // arena vectors: vec(id) = vec_base + id * vstride
     VecPtrs v;
-    PushDesc push_p, push_r, push_s, push_z, push_w;
-    int method;                 // 0 bicgstab, 1 ca_bicgstab, 2 pipe_bicgstab
-    unsigned long long *trace;  // optional [MEGA_TRACE_ITERS][MEGA_TRACE_SLOTS] globaltimer checkpoints of CTA 0 (BICG_MEGA_TRACE)
+    PushPlan push;
+    int method;                 // 0 bicgstab, 1 ca_bicgstab, 2 pipe_bicgstab, 3 pipe_bicgstab_rr
+    int krr, nrr;
+    unsigned long long *trace;  // optional [2][MEGA_TRACE_ITERS][MEGA_TRACE_SLOTS] globaltimer checkpoints (BICG_MEGA_TRACE)
 };
 
-// fuse_q: experimental 4-barrier BiCGStab (q gathered on the fly in the second SpMV), bicgstab only
-int    launch_mega(int threads, bool fuse_q, int grid, size_t smem, const MegaArgs &a, cudaStream_t st);
+int    launch_mega(int threads, int lanes, int grid, size_t smem, const MegaArgs &a, cudaStream_t st);
 int    mega_setup_attributes();
-size_t mega_smem_bytes(int cap, int stages, int threads);
+bool   mega_has_variant(int threads, int lanes);
+size_t mega_smem_bytes(int cap, int stages, int threads, int lanes);
+// per-CTA column ranges of the plan (one launch at plan time)
+void   launch_mega_dep(const unsigned *col, const unsigned *ptr, const int *tile_row, const int *cta_tile, int grid,
+                       int ghost_off, int4 *dep, cudaStream_t st);
 
 } // namespace bicg

@@ -101,21 +101,43 @@ void merge_blocks(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Mat
     }
 }
 
-// Tile plan of the persistent solver kernel (mega.cu): CTA g of `ctas` owns the contiguous rows
-// [rows*g/ctas, rows*(g+1)/ctas), cut into ceil(len/threads) tiles of (almost) equal height.  tile_row gets the first
-// row of every tile plus a final `rows`; cta_tile[g] is the index of CTA g's first tile (cta_tile[ctas] = #tiles).
-// Returns the largest number of entries in any tile.
-unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int threads, std::vector<int> &tile_row,
-                        std::vector<int> &cta_tile)
+// Tile plan of the persistent solver kernel (mega.cu).  CTA g of `ctas` owns a contiguous row range; the ranges are
+// balanced by the bytes an iteration moves for a row -- 24 B per entry (two SpMVs) + 216 B of vector traffic, plus
+// `extra_weight` for every peer the row is pushed to (NVLink stores are slow per SM, and the CTAs at the partition
+// boundary also sit on the critical path of the halo exchange) -- and start at multiples of 16 rows, so every CTA's
+// slice of every vector is 128-byte aligned.  Each range is cut into ceil(len / rows_per_tile) tiles of (almost)
+// equal height.  tile_row gets the first row of every tile plus a final `rows`; cta_tile[g] is the index of CTA g's
+// first tile (cta_tile[ctas] = #tiles).  Returns the largest number of entries in any tile.
+unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int rows_per_tile, const unsigned char *row_extra,
+                        int extra_weight, std::vector<int> &tile_row, std::vector<int> &cta_tile)
 {
     tile_row.clear();
     cta_tile.assign((size_t)ctas + 1, 0);
+    std::vector<int> first((size_t)ctas + 1, rows);
+    first[0] = 0;
+    auto weight = [&](int i) -> long long {
+        return 24ll * (long long)(ptr[i + 1] - ptr[i]) + 216ll + (row_extra ? (long long)extra_weight * row_extra[i] : 0ll);
+    };
+    long long total = 24ll * (long long)(ptr[rows] - ptr[0]) + 216ll * rows;
+    if (row_extra && extra_weight)
+        for (int i = 0; i < rows; ++i) total += (long long)extra_weight * row_extra[i];
+    {
+        long long prefix = 0;         // weight of rows [0, r)
+        int r = 0;
+        for (int g = 1; g < ctas; ++g) {
+            const long long target = (long long)((__int128)total * g / ctas);
+            while (r < rows && prefix + weight(r) / 2 < target) { prefix += weight(r); ++r; }
+            int cut = (int)(((long long)r + 8) / 16 * 16);           // nearest multiple of 16
+            cut = std::min(rows, std::max(cut, first[(size_t)g - 1]));
+            first[(size_t)g] = cut;
+        }
+    }
     unsigned max_tile_nnz = 0;
     for (int g = 0; g < ctas; ++g) {
-        const long long lo = (long long)rows * g / ctas, hi = (long long)rows * (g + 1) / ctas;
+        const int lo = first[(size_t)g], hi = first[(size_t)g + 1];
         cta_tile[(size_t)g] = (int)tile_row.size();
-        const int len = (int)(hi - lo);
-        const int k = (len + threads - 1) / threads;
+        const int len = hi - lo;
+        const int k = (len + rows_per_tile - 1) / rows_per_tile;
         for (int t = 0; t < k; ++t) {
             const int r0 = (int)(lo + (long long)len * t / k), r1 = (int)(lo + (long long)len * (t + 1) / k);
             tile_row.push_back(r0);
@@ -168,11 +190,11 @@ extern "C" long long bicg_plan_merge(const CSR_Matrix *diag, const CSR_Matrix *o
     return (long long)(recv.size() / 4);
 }
 
-extern "C" int bicg_plan_cta_tiles(const unsigned int *ptr, int rows, int ctas, int threads, int *tile_row, int tile_row_cap,
-                                   int *cta_tile, unsigned int *max_tile_nnz)
+extern "C" int bicg_plan_cta_tiles(const unsigned int *ptr, int rows, int ctas, int rows_per_tile, const unsigned char *row_extra,
+                                   int extra_weight, int *tile_row, int tile_row_cap, int *cta_tile, unsigned int *max_tile_nnz)
 {
     std::vector<int> tr, ct;
-    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, threads, tr, ct);
+    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, rows_per_tile, row_extra, extra_weight, tr, ct);
     if ((int)tr.size() > tile_row_cap) return -(int)tr.size();
     std::memcpy(tile_row, tr.data(), tr.size() * sizeof(int));
     std::memcpy(cta_tile, ct.data(), ct.size() * sizeof(int));

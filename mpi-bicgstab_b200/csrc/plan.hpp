@@ -9,8 +9,8 @@ struct HaloRun { int first; int len; int owner; };
 struct PushRunHost { int src; int len; int dst_off; };   // local rows [src, src+len) -> ghost slots dst_off.. on the peer   // global columns [first, first+len) owned by `owner`
 
 int  plan_tiles(const unsigned *ptr, int rows, int rows_per_tile, int cap_nnz, std::vector<int> &tile_row);
-unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int threads, std::vector<int> &tile_row,
-                        std::vector<int> &cta_tile);
+unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int rows_per_tile, const unsigned char *row_extra,
+                        int extra_weight, std::vector<int> &tile_row, std::vector<int> &cta_tile);
 void plan_halo_runs(const CSR_Matrix *offd, const INFO_Matrix *info, int world, int gap, int self,
                     std::vector<HaloRun> &runs);
 

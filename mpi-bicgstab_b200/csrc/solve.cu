@@ -13,6 +13,7 @@
 //   pipe_bicgstab  P1 p,s,z,q,y (+ post 2 dots)  P2 SpMV v=Az (completes it)  P3 x,r,w (+ post 5 dots)  P4 SpMV t=Aw (completes it)
 //   pipe_bicgstab_rr  = pipe, with the replacement iterations of solver.c:498-501, 522-527 as extra SpMVs
 #include "engine.hpp"
+#include "vec_body.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -37,6 +38,8 @@ __global__ void fill_kernel(double *p, int n, double v)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
+
+__global__ void set_coef_kernel(Scalars *s, double al, double be, double om) { s->alpha = al; s->beta = be; s->omega = om; }
 
 inline TailDesc tail_none() { return TailDesc{TAIL_NONE, FIN_NONE, 0, 0, 0, 0, 0}; }
 inline TailDesc tail_allreduce(int fin, int ndot, int npend = 0) { return TailDesc{TAIL_ALLREDUCE, fin, ndot, npend, 0, 0, 0}; }
@@ -79,24 +82,38 @@ struct Seq {
     }
 
     // the persistent kernel runs the whole loop (mega.cu); false: it could not be launched
-    bool mega(int method)
+    bool mega(int method, int krr, int nrr)
     {
         MegaArgs a{};
-        a.sc = m->d_sc; a.partials = m->d_partials; a.hist = m->d_hist; a.comm = m->comm; a.bar = m->d_bar;
+        a.sc = m->d_sc; a.hist = m->d_hist; a.comm = m->comm; a.sync = m->d_msync;
+        for (int p = 0; p < MAX_RANKS; ++p) a.peer_mail[p] = &m->peer_msync[p]->mail[0][0];
+        a.ghost_first = m->d_ghost_first; a.cta_dep = m->mega.d_cta_dep;
         a.val = m->d_val; a.col = m->d_col; a.ptr = m->d_ptr;
         a.tile_row = m->mega.d_tile_row; a.tile_nz = m->mega.d_tile_nz; a.cta_tile = m->mega.d_cta_tile;
         a.cap = m->mega.cap; a.stages = m->mega.stages;
+        a.ghost_off = m->ghost_off; a.l2_hint = c.cfg.l2_hint;
+        a.vec_base = m->vec_base; a.vstride = m->vstride;
         a.v = ptrs();
-        a.push_p = make_push(V_P); a.push_r = make_push(V_R); a.push_s = make_push(V_S);
-        a.push_z = make_push(V_Z); a.push_w = make_push(V_W);
-        a.method = method;
+        a.push.npeers = m->world > 1 ? m->npush : 0;
+        for (int s = 0; s < a.push.npeers; ++s) {
+            const int d = m->push_peer[s];
+            a.push.peer[s] = d;
+            a.push.ghost0[s] = (double *)((char *)m->peer_base[d] + m->peer_vec_off[d]) + m->peer_ghost_off[d];
+            a.push.vstride[s] = m->peer_vstride[d];
+            a.push.runs[s] = m->d_push_runs[s];
+            a.push.nruns[s] = m->push_nruns[s];
+            a.push.hflag_dst[s] = &m->peer_msync[d]->hflag[m->rank][0];
+        }
+        a.method = method; a.krr = krr; a.nrr = nrr;
         a.trace = m->d_trace;
-        const bool fq = c.cfg.mega_fuseq && method == BICG_METHOD_BICGSTAB;
-        int rc = launch_mega(m->mega.threads, fq, m->mega.grid, m->mega.smem, a, c.stream);
+        int rc = launch_mega(m->mega.threads, m->mega.lanes, m->mega.grid, m->mega.smem, a, c.stream);
         if (rc) {
-            // e.g. the grid cannot be co-resident because something else holds SMs: not an error, the
-            // kernel-per-phase path below does the same job
+            // e.g. the grid cannot be co-resident because something else holds SMs.  Single rank: not an error, the
+            // kernel-per-phase path below does the same job.  With peers the ranks must agree on the loop
+            // implementation (its synchronisation protocol), so a local failure is fatal.
             (void)cudaGetLastError();
+            if (m->world > 1) fatal("bicgstab_b200: rank %d could not launch the persistent kernel: %s", m->rank,
+                                    cudaGetErrorString((cudaError_t)rc));
             if (c.cfg.verbose) fprintf(stderr, "[bicg] persistent kernel not launched (%s); using the per-phase kernels\n",
                                        cudaGetErrorString((cudaError_t)rc));
             m->mega.ok = false;
@@ -149,7 +166,6 @@ struct Seq {
         vec(PH_PUSH, tail_none(), V_X);
         spmv(V_X, V_AX, tail_none());                                            // Ax = A x0
         vec(PH_BICG_INIT, tail_allreduce(FIN_BICG_INIT, 1), V_P);                // r, r#, p, (r,r)
-        if (c.cfg.mega_fuseq && c.cfg.mega && m->mega.ok) vec(PH_PUSH, tail_none(), V_R);   // experimental loop gathers r too
     }
     // ---- solver.c:88-120 -------------------------------------------------------------------------------
     void bicgstab_iter()
@@ -305,9 +321,9 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
     if (method == BICG_METHOD_BICGSTAB) seq.bicgstab_init();
     else seq.capipe_init(method != BICG_METHOD_CA);
 
-    bool use_mega = cfg.mega && m->mega.ok && !c.prof_on && method != BICG_METHOD_PIPE_RR;
-    if (use_mega) use_mega = seq.mega(method);
-    const bool use_graph = cfg.graph && !c.prof_on && method != BICG_METHOD_PIPE_RR;
+    bool use_mega = cfg.mega && m->mega.ok && !c.prof_on;
+    if (use_mega) use_mega = seq.mega(method, krr, nrr);
+    const bool use_graph = cfg.graph && !c.prof_on && method != BICG_METHOD_PIPE_RR;   // replacement iterations are host-scheduled
     const int U = std::max(1, cfg.unroll);
     const int batches = (max_iter + U - 1) / U;
     const int DEPTH = 3, RING = 64;
@@ -356,20 +372,25 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
 
     if (hs.error) fatal("bicgstab_b200: rank %d timed out waiting for a peer GPU (halo or reduction mailbox)", m->rank);
     if (m->d_trace && use_mega && method == BICG_METHOD_BICGSTAB) {
-        // BICG_MEGA_TRACE=1: where CTA 0 of the persistent kernel spent its time, averaged over the iterations
+        // BICG_MEGA_TRACE=1: where CTA 0 and the middle CTA of the persistent kernel spent their time, averaged over the iterations
         const int iters = std::min(hs.k - 1, (int)MEGA_TRACE_ITERS);
-        std::vector<unsigned long long> tr((size_t)MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS);
+        std::vector<unsigned long long> tr((size_t)2 * MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS);
         BICG_CUDA(cudaMemcpy(tr.data(), m->d_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        static const char *names[10] = {"spmv s=Ap", "bar alpha", "vec q +push", "bar halo q", "spmv y=Aq", "bar omega",
-                                        "vec x,r", "bar beta", "vec p +push", "bar halo p"};
-        double sum[10] = {0};
-        for (int it = 1; it < iters; ++it)
-            for (int k = 0; k < 10; ++k)
-                sum[k] += (double)(tr[(size_t)it * MEGA_TRACE_SLOTS + k + 1] - tr[(size_t)it * MEGA_TRACE_SLOTS + k]);
-        fprintf(stderr, "[bicg mega trace r%d] us per iteration (CTA 0):", m->rank);
-        double tot = 0;
-        for (int k = 0; k < 10; ++k) { fprintf(stderr, " %s %.1f |", names[k], sum[k] / std::max(1, iters - 1) * 1e-3); tot += sum[k]; }
-        fprintf(stderr, " total %.1f\n", tot / std::max(1, iters - 1) * 1e-3);
+        static const char *names[10] = {"spmv s=Ap", "sync alpha", "vec q +push", "nbr/halo q", "spmv y=Aq", "sync omega",
+                                        "vec x,r", "sync beta", "vec p +push", "nbr/halo p"};
+        for (int who = 0; who < 2; ++who) {
+            double sum[10] = {0};
+            const size_t base = (size_t)who * MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS;
+            for (int it = 1; it < iters; ++it)
+                for (int k = 0; k < 10; ++k)
+                    sum[k] += (double)(tr[base + (size_t)it * MEGA_TRACE_SLOTS + k + 1] - tr[base + (size_t)it * MEGA_TRACE_SLOTS + k]);
+            char line[1024]; int o = 0;
+            o += snprintf(line + o, sizeof(line) - o, "[bicg mega trace r%d] us per iteration (CTA %s):", m->rank, who ? "mid" : "0");
+            double tot = 0;
+            for (int k = 0; k < 10; ++k) { o += snprintf(line + o, sizeof(line) - o, " %s %.2f |", names[k], sum[k] / std::max(1, iters - 1) * 1e-3); tot += sum[k]; }
+            snprintf(line + o, sizeof(line) - o, " total %.2f\n", tot / std::max(1, iters - 1) * 1e-3);
+            fputs(line, stderr);
+        }
     }
 
     bicg_stats st{};
@@ -457,6 +478,89 @@ int spmv_time(bicg_matrix *m, int reps, double *ms_out, double *bytes_out)
 }
 
 } // namespace bicg
+
+// ------------------------------------------------------------------------------------------------
+// test hooks (K-level parity: single fused phases and epilogue dots on caller-supplied vectors; single rank)
+// ------------------------------------------------------------------------------------------------
+extern "C" int bicg_debug_vec_phase(bicg_matrix *m, int phase, const double coef[3], double *vecs, double dots[8])
+{
+    using namespace bicg;
+    Context &c = ctx();
+    c.ensure();
+    if (m->world != 1 || phase < 0 || phase >= PH_PUSH) return -1;
+    const size_t vb = (size_t)m->n_loc * sizeof(double);
+    for (int id = 0; id < V_COUNT; ++id)
+        BICG_CUDA(cudaMemcpyAsync(m->vec(id), vecs + (size_t)id * m->n_loc, vb, cudaMemcpyHostToDevice, c.stream));
+    reset_state_kernel<<<1, 1, 0, c.stream>>>(m->d_sc, c.cfg.tol, c.cfg.max_iter);
+    set_coef_kernel<<<1, 1, 0, c.stream>>>(m->d_sc, coef[0], coef[1], coef[2]);
+    static const int ndots[PH_PUSH] = {phase_ndot(PH_BICG_INIT), phase_ndot(PH_BICG_Q), phase_ndot(PH_BICG_XR), phase_ndot(PH_BICG_P),
+                                       phase_ndot(PH_INIT_R), phase_ndot(PH_CA_PS), phase_ndot(PH_QY), phase_ndot(PH_CA_XR),
+                                       phase_ndot(PH_PIPE_1), phase_ndot(PH_PIPE_3), phase_ndot(PH_RR_P), phase_ndot(PH_RR_X),
+                                       phase_ndot(PH_RR_R), phase_ndot(PH_RR_DOTS)};
+    const int nd = ndots[phase];
+    Seq seq(m);
+    seq.vec(phase, nd > 0 ? tail_pend(nd, 0) : tail_none());
+    for (int id = 0; id < V_COUNT; ++id)
+        BICG_CUDA(cudaMemcpyAsync(vecs + (size_t)id * m->n_loc, m->vec(id), vb, cudaMemcpyDeviceToHost, c.stream));
+    Scalars hs;
+    BICG_CUDA(cudaMemcpyAsync(&hs, m->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c.stream));
+    BICG_CUDA(cudaStreamSynchronize(c.stream));
+    for (int k = 0; k < 8; ++k) dots[k] = k < nd ? hs.pend[k] : 0.0;
+    return nd;
+}
+
+// y (arena vector V_S) = A x (V_P) with the solver's fused epilogue dots.  epi 1: (r#,y); 2: (r,y),(y,y); 3: (r#,r),(r#,y),(r#,s),(r#,z)
+// with s, z read from V_S' = V_AX and V_Z (y itself goes to V_W for epi 3, as in ca_bicgstab).  vecs: V_COUNT x n_loc in/out.
+extern "C" int bicg_debug_spmv_epi(bicg_matrix *m, int epi, double *vecs, double dots[8])
+{
+    using namespace bicg;
+    Context &c = ctx();
+    c.ensure();
+    if (m->world != 1 || epi < 0 || epi > 3) return -1;
+    const size_t vb = (size_t)m->n_loc * sizeof(double);
+    for (int id = 0; id < V_COUNT; ++id)
+        BICG_CUDA(cudaMemcpyAsync(m->vec(id), vecs + (size_t)id * m->n_loc, vb, cudaMemcpyHostToDevice, c.stream));
+    reset_state_kernel<<<1, 1, 0, c.stream>>>(m->d_sc, c.cfg.tol, c.cfg.max_iter);
+    Seq seq(m);
+    const double *Y = nullptr;
+    int nd = 0;
+    if (epi == 0) seq.spmv(V_P, V_S, tail_none());
+    else if (epi == 1) { nd = 1; seq.spmv(V_P, V_S, tail_pend(1, 0), 1, m->vec(V_RH), Y); }
+    else if (epi == 2) { nd = 2; seq.spmv(V_P, V_S, tail_pend(2, 0), 2, m->vec(V_R), Y, Y, Y); }
+    else { nd = 4; seq.spmv(V_P, V_W, tail_pend(4, 0), 4, m->vec(V_RH), m->vec(V_R), m->vec(V_RH), Y, m->vec(V_RH), m->vec(V_AX),
+                            m->vec(V_RH), m->vec(V_Z)); }
+    for (int id = 0; id < V_COUNT; ++id)
+        BICG_CUDA(cudaMemcpyAsync(vecs + (size_t)id * m->n_loc, m->vec(id), vb, cudaMemcpyDeviceToHost, c.stream));
+    Scalars hs;
+    BICG_CUDA(cudaMemcpyAsync(&hs, m->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c.stream));
+    BICG_CUDA(cudaStreamSynchronize(c.stream));
+    for (int k = 0; k < 8; ++k) dots[k] = k < nd ? hs.pend[k] : 0.0;
+    return nd;
+}
+
+// own part of arena vector `id` / the solver scalars as the last solve left them
+extern "C" int bicg_debug_get_vec(bicg_matrix *m, int id, double *out)
+{
+    using namespace bicg;
+    Context &c = ctx();
+    c.ensure();
+    if (id < 0 || id >= V_COUNT) return -1;
+    BICG_CUDA(cudaMemcpyAsync(out, m->vec(id), (size_t)m->n_loc * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    BICG_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+extern "C" int bicg_debug_get_scalars(bicg_matrix *m, double out[13])
+{
+    using namespace bicg;
+    Context &c = ctx();
+    c.ensure();
+    Scalars hs;
+    BICG_CUDA(cudaMemcpyAsync(&hs, m->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c.stream));
+    BICG_CUDA(cudaStreamSynchronize(c.stream));
+    const double v[13] = {hs.rTr, hs.rTr_old, hs.rTs, hs.rTy, hs.yTy, hs.rTw, hs.wTw, hs.rTz, hs.dot_r, hs.dot_zero, hs.alpha, hs.beta, hs.omega};
+    for (int k = 0; k < 13; ++k) out[k] = v[k];
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // profile: one solve with plain stream launches, every launch bracketed by events

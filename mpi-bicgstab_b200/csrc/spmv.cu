@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(CTHREADS + 32, 1) spmv_ws_kernel(const __grid_
                     v[u] = sval[idx];
                 }
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) xv[u] = __ldg(x + c[u]);
+                for (int u = 0; u < UNR; ++u) xv[u] = ld_coherent(x + c[u]);
 #pragma unroll
                 for (int u = 0; u < UNR; ++u)
                     if (j + u * LANES < e) acc = fma(v[u], xv[u], acc);
@@ -220,12 +220,12 @@ __global__ void __launch_bounds__(256) spmv_rowsplit_kernel(const __grid_constan
         for (; j + 3 * LANES < pe; j += 4 * LANES) {
             const unsigned c0 = col[j], c1 = col[j + LANES], c2 = col[j + 2 * LANES], c3 = col[j + 3 * LANES];
             const double v0 = val[j], v1 = val[j + LANES], v2 = val[j + 2 * LANES], v3 = val[j + 3 * LANES];
-            acc = fma(v0, __ldg(x + c0), acc);
-            acc = fma(v1, __ldg(x + c1), acc);
-            acc = fma(v2, __ldg(x + c2), acc);
-            acc = fma(v3, __ldg(x + c3), acc);
+            acc = fma(v0, ld_coherent(x + c0), acc);
+            acc = fma(v1, ld_coherent(x + c1), acc);
+            acc = fma(v2, ld_coherent(x + c2), acc);
+            acc = fma(v3, ld_coherent(x + c3), acc);
         }
-        for (; j < pe; j += LANES) acc = fma(val[j], __ldg(x + col[j]), acc);
+        for (; j < pe; j += LANES) acc = fma(val[j], ld_coherent(x + col[j]), acc);
         acc = lanes_sum<LANES>(acc);
         if (valid && lane == 0) {
             a.y[row] = acc;

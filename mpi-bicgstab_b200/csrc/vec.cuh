@@ -16,6 +16,11 @@ struct PushDesc {
     int            nruns[MAX_RANKS - 1];
 };
 
+// arena vectors
+enum VecId { V_X = 0, V_R, V_RH, V_P, V_S, V_Y, V_W, V_V, V_T, V_B, V_AX, V_COUNT };
+// V_Y doubles as z (the CA / pipelined variants call the same storage z)
+constexpr int V_Z = V_Y;
+
 // vector roles (pointers to the own part of each arena vector; unused ones are null)
 struct VecPtrs {
     double *x, *r, *rh, *p, *s, *y, *z, *w, *v, *t, *b, *ax;
@@ -46,7 +51,6 @@ enum Phase : int {
     PH_RR_R,            // r=b-Ax                                    [push r]
     PH_RR_DOTS,         // 5 dots                                    [push w]
     PH_PUSH,            // push only
-    PH_BICG_XR_Q,       // like PH_BICG_XR with q in its own vector (ax) -- experimental 4-barrier loop of mega.cu
     PH_COUNT
 };
 

@@ -34,7 +34,7 @@ template <> __device__ __forceinline__ void st<4>(double *p, int i, const Pk<4> 
 
 __host__ __device__ constexpr int phase_ndot(int ph)
 {
-    return ph == PH_BICG_INIT ? 1 : ph == PH_BICG_XR ? 2 : ph == PH_BICG_XR_Q ? 2 : ph == PH_INIT_R ? 1 : ph == PH_QY ? 2
+    return ph == PH_BICG_INIT ? 1 : ph == PH_BICG_XR ? 2 : ph == PH_INIT_R ? 1 : ph == PH_QY ? 2
          : ph == PH_CA_XR ? 1 : ph == PH_PIPE_1 ? 2 : ph == PH_PIPE_3 ? 5 : ph == PH_RR_DOTS ? 5 : 0;
 }
 
@@ -59,6 +59,26 @@ template <int W_, int STRIDE> struct Strided {
     {
 #pragma unroll
         for (int k = 0; k < W_; ++k) p[i + k * STRIDE] = a.v[k];
+    }
+};
+
+// K double2 accesses STRIDE doubles apart (persistent kernel: K independent 16-byte loads in flight per vector)
+template <int K, int STRIDE> struct Pairs {
+    static constexpr int W = 2 * K;
+    static __device__ __forceinline__ Pk<W> ld(const double *p, int i)
+    {
+        Pk<W> r;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double2 t = *reinterpret_cast<const double2 *>(p + i + k * STRIDE);
+            r.v[2 * k] = t.x; r.v[2 * k + 1] = t.y;
+        }
+        return r;
+    }
+    static __device__ __forceinline__ void st(double *p, int i, const Pk<W> &a)
+    {
+#pragma unroll
+        for (int k = 0; k < K; ++k) *reinterpret_cast<double2 *>(p + i + k * STRIDE) = make_double2(a.v[2 * k], a.v[2 * k + 1]);
     }
 };
 
@@ -89,17 +109,6 @@ __device__ __forceinline__ void body(const VecPtrs &v, int i, const Coef &c, dou
             x.v[k] = fma(c.al, p.v[k], x.v[k]);
             x.v[k] = fma(c.om, r.v[k], x.v[k]);
             r.v[k] = fma(-c.om, y.v[k], r.v[k]);
-            dot[0] = fma(r.v[k], r.v[k], dot[0]);
-            dot[1] = fma(rh.v[k], r.v[k], dot[1]);
-        }
-        L::st(v.x, i, x); L::st(v.r, i, r);
-    } else if constexpr (PH == PH_BICG_XR_Q) {
-        Pk<W> x = L::ld(v.x, i), p = L::ld(v.p, i), q = L::ld(v.ax, i), y = L::ld(v.y, i), rh = L::ld(v.rh, i), r;
-#pragma unroll
-        for (int k = 0; k < W; ++k) {
-            x.v[k] = fma(c.al, p.v[k], x.v[k]);
-            x.v[k] = fma(c.om, q.v[k], x.v[k]);
-            r.v[k] = fma(-c.om, y.v[k], q.v[k]);
             dot[0] = fma(r.v[k], r.v[k], dot[0]);
             dot[1] = fma(rh.v[k], r.v[k], dot[1]);
         }

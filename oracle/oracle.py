@@ -55,6 +55,10 @@ def lib():
         L.orc_spmv_ld.argtypes = [C.c_int, _dp, _up, _up, _dp, _dp]
         L.orc_ddot.restype = C.c_double
         L.orc_ddot.argtypes = [C.c_int, _dp, _dp]
+        L.orc_daxpy.restype = None
+        L.orc_daxpy.argtypes = [C.c_int, C.c_double, _dp, _dp]
+        L.orc_dscal.restype = None
+        L.orc_dscal.argtypes = [C.c_int, C.c_double, _dp]
         L.orc_partition.restype = None
         L.orc_partition.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _lib = L
@@ -97,6 +101,27 @@ def solve(method, n, ptr, col, val, b, x0=None, P=1, tol=1e-15, max_iter=1000, k
     else:
         raise ValueError(method)
     return {"iters": it, "x": x, "r": r, "hist": hist[:it + 1]}
+
+
+# ---- BLAS-1 restatements (vector.c:3-27), in place on contiguous float64 arrays ---------------------------
+def _f64(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return _p(a, _dp)
+
+
+def daxpy(a, x, y):
+    """y += a * x   (vector.c:3-7)"""
+    lib().orc_daxpy(y.size, float(a), _f64(x), _f64(y))
+
+
+def dscal(a, x):
+    """x *= a       (vector.c:17-21)"""
+    lib().orc_dscal(x.size, float(a), _f64(x))
+
+
+def ddot(x, y):
+    """sum x_i y_i, left to right (vector.c:9-15)"""
+    return float(lib().orc_ddot(x.size, _f64(x), _f64(y)))
 
 
 def partition(n, P):

@@ -38,7 +38,7 @@ def main():
         y_ref = O.spmv(n, ptr, col, val, xg, long_double=True)[lo:lo + nloc]
         assert np.abs(y - y_ref).max() <= 1e-13 * np.abs(y_ref).max(), ("spmv", kind, rank)
         b_ref = O.spmv(n, ptr, col, val, np.ones(n), P=world)
-        for method, mega in [(m_, g_) for m_ in METHODS for g_ in ((1, 0) if not m_.endswith("rr") else (0,))]:
+        for method, mega in [(m_, g_) for m_ in METHODS for g_ in (1, 0)]:
             kw = RR if method.endswith("rr") else {}
             B.set_options(tol=TOL, max_iter=600, mega=mega)
             b = dm.spmv(np.ones(nloc))

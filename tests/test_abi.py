@@ -185,20 +185,31 @@ def test_options_and_unknown_keys(B):
     assert B.lib.bicg_comm_rank() == 0 and B.lib.bicg_comm_world() == 1 and B.lib.bicg_comm_selftest() == 0
 
 
-@pytest.mark.parametrize("rows,ctas,threads", [(1601613, 148, 512), (200264, 148, 512), (343, 148, 512), (1, 148, 256),
-                                                (5000, 7, 256), (148 * 512, 148, 512)])
-def test_persistent_kernel_tile_plan(B, rows, ctas, threads):
-    """plan_cta_tiles (mega.cu's work split): contiguous, complete, balanced, every tile fits the CTA's threads."""
+@pytest.mark.parametrize("rows,ctas,rpt", [(1601613, 148, 512), (200264, 148, 512), (343, 148, 512), (1, 148, 256),
+                                            (5000, 7, 256), (148 * 512, 148, 512), (2_000_000, 148, 64)])
+@pytest.mark.parametrize("extra", [0, 600])
+def test_persistent_kernel_tile_plan(B, rows, ctas, rpt, extra):
+    """plan_cta_tiles (mega.cu's work split): contiguous, complete, 16-row aligned, balanced by per-row work
+    24*nnz + 216 (+ extra per pushed row), every tile fits the CTA's rows-per-tile."""
     rng = np.random.default_rng(rows)
     ptr = np.concatenate([[0], np.cumsum(rng.integers(0, 20, size=rows))]).astype(np.uint32)
+    row_extra = np.zeros(rows, dtype=np.uint8)
+    row_extra[: rows // 10] = 1                                   # the first tenth of the rows is pushed to a peer
     cap = rows + ctas + 8
     tr = (C.c_int * cap)(); ct = (C.c_int * (ctas + 1))(); mx = C.c_uint()
-    nt = B.lib.bicg_plan_cta_tiles(ptr.ctypes.data_as(C.POINTER(C.c_uint)), rows, ctas, threads, tr, cap, ct, C.byref(mx))
+    nt = B.lib.bicg_plan_cta_tiles(ptr.ctypes.data_as(C.POINTER(C.c_uint)), rows, ctas, rpt,
+                                   row_extra.ctypes.data_as(C.c_void_p) if extra else None, extra, tr, cap, ct, C.byref(mx))
     t = np.array(tr[:nt + 1]); c = np.array(ct[:])
-    assert t[0] == 0 and t[-1] == rows and np.all(np.diff(t) > 0) and np.all(np.diff(t) <= threads)
+    assert t[0] == 0 and t[-1] == rows and np.all(np.diff(t) > 0) and np.all(np.diff(t) <= rpt)
     assert c[0] == 0 and c[-1] == nt and np.all(np.diff(c) >= 0)
-    per_cta = t[c[1:]] - t[c[:-1]]                               # rows owned by every CTA
-    assert per_cta.sum() == rows and per_cta.max() - per_cta.min() <= 1
+    first = t[c]                                                  # first row of every CTA (then `rows`)
+    assert first[0] == 0 and first[-1] == rows and np.all(np.diff(first) >= 0)
+    assert np.all(first[:-1] % 16 == 0)                           # 128-byte aligned vector slices
+    w = 24 * np.diff(ptr.astype(np.int64)) + 216 + extra * row_extra.astype(np.int64)
+    pw = np.concatenate([[0], np.cumsum(w)])
+    per_cta = pw[first[1:]] - pw[first[:-1]]
+    ideal = pw[-1] / ctas
+    assert per_cta.max() <= ideal + 17 * w.max()                  # within one alignment granule of the ideal share
     for g in range(ctas):                                        # tiles of one CTA have (almost) equal height
         h = np.diff(t[c[g]:c[g + 1] + 1])
         assert h.size == 0 or h.max() - h.min() <= 1

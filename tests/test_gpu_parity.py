@@ -218,24 +218,3 @@ def test_reference_main_c_runs_on_the_library(B, O, tmp_path):
         assert abs(it - ref["iters"]) <= 2, (method, it, ref["iters"])
         assert re.search(r"Iteration: 10, Residual: \d\.\d{6}e[-+]\d\d", out)
         assert float(re.search(r"Final r\s*:\s*(\S+)", out).group(1)) <= 1e-10
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("BICG_TEST_EXPERIMENTAL"),
-                    reason="experimental path (BICG_MEGA_FUSEQ); set BICG_TEST_EXPERIMENTAL=1 to include it")
-@pytest.mark.parametrize("name,kind,g,p0", SMALL_CASES)
-def test_experimental_four_barrier_bicgstab(B, O, name, kind, g, p0):
-    """EXPERIMENTAL, off by default: q gathered on the fly in the second SpMV of the persistent kernel."""
-    blk, n, ptr, col, val = global_csr(B, kind, g, p0)
-    B.set_options(tol=TOL, max_iter=600, mega=1, mega_fuseq=1)
-    try:
-        b = B.spmv_ovlap(blk, np.ones(n))
-        x = np.zeros(n)
-        it = B.bicgstab(blk, x, b)
-        hist = B.last_history()
-    finally:
-        B.set_options(mega_fuseq=0)
-    ref = O.solve("bicgstab", n, ptr, col, val, O.spmv(n, ptr, col, val, np.ones(n)), tol=TOL, max_iter=600)
-    m = min(10, it, ref["iters"])
-    got, want = np.sqrt(hist[1:m + 1]), np.sqrt(ref["hist"][1:m + 1])
-    assert np.all(np.abs(got - want) <= 1e-10 * want + H_FLOOR)
-    assert abs(it - ref["iters"]) <= 2 and np.abs(x - 1).max() < 1e-6

@@ -1,4 +1,5 @@
-"""Per-iteration time of each loop implementation on one workload (single or multi rank)."""
+"""Per-iteration time of each loop implementation on one workload (single or multi rank).
+usage: quick_perf.py [methods...]   env: QP_KIND/QP_G/QP_P0 (workload), QP_MODES=mega,graph, QP_ITERS, BICG_* options"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,17 +14,25 @@ if world > 1:
 B.set_options(device=local, quiet=1)
 if world > 1:
     B.comm_init_torch()
-blk = B.gen_block("stencil15", 117, 14.0, rank=rank, world=world)
+kind = os.environ.get("QP_KIND", "stencil15"); g = int(os.environ.get("QP_G", "117")); p0 = float(os.environ.get("QP_P0", "14.0"))
+if kind == "random":
+    g *= world
+iters = int(os.environ.get("QP_ITERS", "300"))
+modes = os.environ.get("QP_MODES", "mega,graph").split(",")
+blk = B.gen_block(kind, g, p0, rank=rank, world=world)
 dm = B.DeviceMatrix(blk)
 nl = blk.n_loc
 for method in (sys.argv[1:] or ["bicgstab", "ca_bicgstab", "pipe_bicgstab"]):
-    for mode, kw in (("mega", dict(mega=1)), ("graph", dict(mega=0, graph=1))):
-        B.set_options(tol=0.0, max_iter=300, **kw)
+    for mode in modes:
+        kw = dict(mega=1) if mode == "mega" else dict(mega=0, graph=1)
+        B.set_options(tol=0.0, max_iter=iters, **kw)
         for rep in range(2):
             b = dm.spmv(np.ones(nl)); x = np.zeros(nl)
-            it, st = dm.solve(method, x, b)
+            kwargs = dict(krr=50, nrr=3) if method.endswith("rr") else {}
+            it, st = dm.solve(method, x, b, **kwargs)
         if rank == 0:
-            print(f"[N={world}] {method:14s} {mode:6s} {st['loop_ms'] / it * 1e3:7.1f} us/it  {it / st['loop_ms'] * 1e3:8.0f} it/s", flush=True)
+            print(f"[N={world}] {kind} {method:17s} {mode:6s} {st['loop_ms'] / it * 1e3:7.2f} us/it  {it / st['loop_ms'] * 1e3:8.0f} it/s  "
+                  f"launches={st['kernel_launches']} res={st['final_res']:.3e}", flush=True)
 dm.destroy()
 if world > 1:
     B.comm_finalize(); dist.destroy_process_group()
