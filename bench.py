@@ -9,13 +9,19 @@ One STEP = one complete solve of the workload (b = A*1, x0 = 0, to BICG_TOL / MA
           library's stream around the K solves, max over ranks)
   e2e   : the same metric through the reference-facing call bicgstab(A_diag, A_offd, A_info, x, r) on pinned
           HOST buffers with the upload cache disabled: every step uploads the matrix and the vectors and reads
-          x and r back (wall clock around K calls, device idle on both sides)
-  roofline    : the fused SpMV + dot kernel (dominant kernel of every variant), algorithmic bytes
-                12*nnz + 28*n_loc per launch (SURVEY.md 8(d) phase P1) / average launch time from CUDA events
+          x and r back (wall clock around K calls, device idle on both sides).  e2e_pageable: the same with plain
+          malloc'ed buffers (what the reference's main.c:81-107 passes).  first_call_ms: the very first upload +
+          plan (SpMV autotune included), which the warm-up otherwise hides.
+  roofline    : the kernel that runs in the timed region -- the persistent solver kernel (one launch per solve):
+                iterations x per-iteration algorithmic bytes / the library's CUDA-event time of
+                the loop; the fused SpMV + dot kernel is timed live beside it (roofline.spmv_kernel)
+  parity      : on EVERY line (every N): H-level max relative error of the first 10 residual-history entries
+                against the oracle's P = N emulation on the same matrix, and iterations-to-tolerance against the
+                reference's own sources run with P = N ranks (oracle/_ref/ref_driver_*)
   cpu_baseline: the reference's own sources (oracle/_ref, compiled in place) on this box's host cores, bounded
                 sample = the first REF_ITERS iterations of the same solve
 
---impl reference times that CPU build alone (rank 0 only under torchrun).
+--impl reference times that CPU build alone (rank 0 only under torchrun); it never loads the product library.
 """
 import argparse
 import json
@@ -44,7 +50,7 @@ WORKLOADS = {
                    label="random CSR, 2,000,000 rows per GPU x 32 nnz/row, b=A*1, x0=0, tol 1e-8"),
 }
 BYTES_PER_ITER_N = {"bicgstab": 160, "ca_bicgstab": 216, "pipe_bicgstab": 232}
-REF_ITERS = 20
+REF_ITERS = 100        # iterations per reference step: ~1-2 s of CPU work per step, init SpMV amortised over 100
 
 
 def measured_peak():
@@ -124,30 +130,67 @@ def pinned_block(B, blk, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------------
+GEN_KIND = {"stencil15": 0, "laplace5": 1, "random": 2, "convdiff": 3}
+
+
+def _ref_flavour(O, gen):
+    """BASELINE.md builds the CPU baseline with -march=native.  oracle/_ref/ref_driver_native was compiled in the dev
+    container; if this host's CPU cannot execute it (SIGILL on a tiny real solve) fall back to the portable
+    x86-64-v3 build."""
+    with tempfile.TemporaryDirectory() as td:
+        tiny = os.path.join(td, "tiny.bin")
+        try:
+            subprocess.run([gen, "0", "8", "14.0", tiny], check=True, capture_output=True, timeout=60)
+        except Exception:
+            return None
+        for flavour in ("native", "fast"):
+            if not os.path.exists(os.path.join(O.REF_DIR, f"ref_driver_{flavour}")):
+                continue
+            try:
+                r = O.ref_driver("bicgstab", tiny, P=1, tol=0.0, max_iter=3, flavour=flavour, want_vectors=False, timeout=60)
+                if r["iters"] == 3:
+                    return flavour
+            except Exception:
+                pass
+    return None
+
+
 class RefRunner:
-    """The reference's own CPU code (oracle/_ref/ref_driver_fast + mini-MPI) on the same input.  The matrix is
-    written once to a binary file in /dev/shm; every run() is one `ref_driver` process tree."""
+    """The reference's own CPU code (oracle/_ref/ref_driver_* + mini-MPI) on the same input.  The matrix is written
+    once to a binary file in /dev/shm by the stand-alone generator oracle/gen_csr (same generator source as the
+    library, but no product .so is loaded in this arm); every run() is one `ref_driver` process tree."""
 
     def __init__(self, w, cores=None):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O
-        import mpi_bicgstab_b200 as B
         self.O, self.w = O, w
-        self.ok = O.have_ref("ref_driver_fast")
+        gen = os.path.join(ROOT, "oracle", "gen_csr")
+        self.flavour = _ref_flavour(O, gen) if os.path.exists(gen) else None
+        self.ok = self.flavour is not None
         if not self.ok:
             return
+        self.march = {"native": "-march=native (built in the dev container)", "fast": "-march=x86-64-v3"}[self.flavour]
         self.cores = cores or min(len(os.sched_getaffinity(0)), 64)
-        blk = B.gen_block(w["kind"], w["g"], w["p0"])
-        ptr, col, val = B.block_to_global_csr(blk)
         self.td = tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         self.file = os.path.join(self.td.name, "a.bin")
-        O.write_csr_bin(self.file, blk.n, ptr, col, val)
-        blk.free()
+        subprocess.run([gen, str(GEN_KIND[w["kind"]]), str(int(w["g"])), repr(float(w["p0"])), self.file], check=True,
+                       capture_output=True, timeout=1800)
+
+    def load_csr(self):
+        """(n, ptr, col, val) of the file the reference solves (oracle.py: write_csr_bin layout)."""
+        with open(self.file, "rb") as f:
+            n, nnz = (int(v) for v in np.fromfile(f, dtype=np.int64, count=2))
+            ptr = np.fromfile(f, dtype=np.uint32, count=n + 1)
+            col = np.fromfile(f, dtype=np.uint32, count=nnz)
+            if (n + 1 + nnz) % 2:
+                np.fromfile(f, dtype=np.uint32, count=1)
+            val = np.fromfile(f, dtype=np.float64, count=nnz)
+        return n, ptr, col, val
 
     def run(self, n_iters, cores=None):
         cores = cores or self.cores
         res = self.O.ref_driver(self.w["method"], self.file, P=cores, rhs="a1", tol=0.0, max_iter=n_iters,
-                                flavour="fast", want_vectors=False, pin=True, timeout=1800)
+                                flavour=self.flavour, want_vectors=False, pin=True, timeout=1800)
         res["cores"] = cores
         return res
 
@@ -170,22 +213,50 @@ class RefRunner:
         self.tried = tried
         return self.cores
 
+    def solve_to_tol(self, P, tol, max_iter):
+        """Full solve with P ranks: the reference's iteration count for the parity object."""
+        return self.O.ref_driver(self.w["method"], self.file, P=P, rhs="a1", tol=tol, max_iter=max_iter,
+                                 flavour=self.flavour, want_vectors=False, pin=True, timeout=1800)
+
     def close(self):
         if self.ok:
             self.td.cleanup()
 
 
-def reference_sample(w, n_iters):
-    rr = RefRunner(w)
-    if not rr.ok:
-        return None
+def reference_sample(rr, n_iters):
+    rr.pick_cores()                        # also pages the file in and warms the cores
+    res = rr.run(n_iters)
+    res["tried"] = rr.tried
+    res["march"] = rr.march
+    return res
+
+
+def parity_object(rr, w, world, hist, iters):
+    """Driver-visible parity at the benchmark's own size and rank count: H-level (first 10 entries of the residual
+    history vs the oracle's P = world emulation, SURVEY.md 8(c): <= 1e-10 relative) and C-level (iterations to tol vs
+    the reference's own sources run with P = world ranks: within max(2, 2 %))."""
+    O = rr.O
+    n, ptr, col, val = rr.load_csr()
+    method = w["method"]
+    t0 = time.perf_counter()
+    b = O.spmv(n, ptr, col, val, np.ones(n), P=world)
+    m = min(10, iters)
+    ref10 = O.solve(method, n, ptr, col, val, b, P=world, tol=w["tol"], max_iter=m)
+    m = min(m, ref10["iters"])
+    got, want = np.sqrt(np.asarray(hist[1:m + 1])), np.sqrt(ref10["hist"][1:m + 1])
+    rel = float(np.max(np.abs(got - want) / want)) if m else 0.0
+    out = {"h_level_max_rel": rel, "h_level_iters": int(m), "h_level_tol": 1e-10, "h_level_ok": bool(rel <= 1e-10),
+           "h_level_oracle": f"oracle/liboracle.so, P={world} rank emulation (pinned bitwise to the compiled reference)",
+           "iters": int(iters), "ref_iters": None, "ref_P": world, "c_level_rule": "max(2, 2 %)"}
     try:
-        rr.pick_cores()                        # also pages the file in and warms the cores
-        res = rr.run(n_iters)
-        res["tried"] = rr.tried
-        return res
-    finally:
-        rr.close()
+        full = rr.solve_to_tol(world, w["tol"], w["max_iter"])
+        out["ref_iters"] = int(full["iters"])
+        out["c_level_ok"] = bool(abs(iters - full["iters"]) <= max(2, int(0.02 * full["iters"])))
+        out["ref_source"] = f"oracle/_ref/ref_driver_{rr.flavour} (the reference's own solver.c/matrix.c/vector.c), {world} ranks"
+    except Exception as exc:
+        out["ref_source"] = f"reference run failed: {exc!r}"
+    out["seconds"] = round(time.perf_counter() - t0, 1)
+    return out
 
 
 def run_reference(args, w):
@@ -194,7 +265,7 @@ def run_reference(args, w):
         return
     rr = RefRunner(w)
     if not rr.ok:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_fast is not built"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_* or oracle/gen_csr is not built"}))
         return
     steps, times, its = args.steps, [], 0
     try:
@@ -214,7 +285,7 @@ def run_reference(args, w):
                        "sample": f"first {REF_ITERS} iterations of the solve per step (reference's own timed region, solver.c:69-132)"},
             "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": rr.cores, "kind": "reference",
                              "sample": f"{REF_ITERS} iterations/step x {steps} steps, {rr.cores} ranks (fork+shm mini-MPI; fastest of "
-                                       f"s/iter by ranks {rr.tried}), gcc -O3 -march=x86-64-v3"},
+                                       f"s/iter by ranks {rr.tried}), gcc -O3 {rr.march}"},
             "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -251,7 +322,8 @@ def run_b200(args, w):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ.pop("NCCL_DEBUG", None)           # NCCL's version banner goes to stdout; stdout carries ONE JSON line
+    if os.environ.get("NCCL_DEBUG"):             # keep NCCL's log (the driver reads the rank count from it), but on stderr:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly ONE JSON line
     full_affinity = bind_near_gpu(local)
     torch.cuda.set_device(local)
     B.set_options(device=local, quiet=1)
@@ -264,7 +336,10 @@ def run_b200(args, w):
     blk = B.gen_block(w["kind"], n_glob_g, w["p0"], rank=rank, world=world)
     n_loc, n = blk.n_loc, blk.n
     B.set_options(tol=w["tol"], max_iter=w["max_iter"])
-    dm = B.DeviceMatrix(blk)                                   # upload + plan (collective)
+    t_first = time.perf_counter()
+    dm = B.DeviceMatrix(blk)                                   # upload + plan (collective); first call: SpMV autotune too
+    B.lib.bicg_synchronize()
+    first_call_ms = 1e3 * (time.perf_counter() - t_first)
     stream = torch.cuda.ExternalStream(B.lib.bicg_stream(), device=torch.device("cuda", local))
 
     def barrier():
@@ -308,6 +383,8 @@ def run_b200(args, w):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         final_res, converged = st.final_res, st.converged
+        hist = B.last_history().copy()          # full-precision residual history of the last resident solve (parity object)
+        last_iters = int(st.iters)
 
         # roofline of the dominant kernel, measured live (per rank; rank 0 reported)
         peak, peak_src = measured_peak()
@@ -337,7 +414,27 @@ def run_b200(args, w):
         t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
+    # the same call on plain malloc'ed (pageable) buffers -- what the reference's main.c hands over (main.c:81-107)
+    xp, rp = np.zeros(n_loc), np.zeros(n_loc)
+    pg_iters, t_pg, pg_steps = 0, 0.0, max(1, min(args.steps, 3))
+    for s in range(1 + pg_steps):
+        xp[:] = 0.0; rp[:] = b_host
+        barrier()
+        t0 = time.perf_counter()
+        it = B.solve(method, blk, xp, rp)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if s >= 1:
+            pg_iters += it; t_pg += dt
+    if world > 1:
+        t = torch.tensor([t_pg], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_pg = float(t.item())
     B.set_options(cache=1)
+    dm.destroy()
+    if world > 1:                      # collective teardown first: rank 0 then spends up to a minute in the CPU legs alone
+        B.comm_finalize()
+        dist.destroy_process_group()
 
     if rank == 0:
         nnz_glob = int(blk.info.nz) if w["kind"] != "random" else n * int(w["p0"])
@@ -383,27 +480,44 @@ def run_b200(args, w):
                        "solver_effective_GBps": bytes_iter * iters / (ms * 1e-3) / 1e9},
             "clocks": clocks,
             "e2e": {"value": e2e_iters / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "host_buffers": "pinned (cudaHostAlloc), upload cache off: matrix + vectors re-uploaded every step"},
+            "e2e_pageable": {"value": pg_iters / t_pg, "unit": "iterations/s", "ms_per_step": 1e3 * t_pg / pg_steps,
+                             "steps": pg_steps, "host_buffers": "plain malloc (what main.c:81-107 passes), upload cache off"},
+            "first_call_ms": first_call_ms,
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
-        if world == 1 and not args.no_cpu:
+        line["roofline"]["traffic_source"] = "profiles/spmv_traffic.json (ncu dram__bytes of the same kernel on the same matrix), not measured in this run"
+        rr = None
+        if not args.no_cpu:
             try:
                 os.sched_setaffinity(0, full_affinity)      # the CPU reference may use every core of the box
-                r = reference_sample(w, REF_ITERS)
+                rr = RefRunner(w)
+                if not rr.ok:
+                    rr = None
+            except Exception as exc:
+                line["parity"] = {"error": f"reference runner unavailable: {exc!r}"}
+                rr = None
+        if rr is not None:
+            try:
+                line["parity"] = parity_object(rr, w, world, hist, last_iters)
+            except Exception as exc:
+                line["parity"] = {"error": repr(exc)}
+        if world == 1 and rr is not None:
+            try:
+                r = reference_sample(rr, REF_ITERS)
                 if r:
                     line["cpu_baseline"] = {"value": 1.0 / r["avg_time_per_iter_s"], "unit": "iterations/s",
                                             "cores": r["cores"], "kind": "reference",
                                             "sample": f"first {REF_ITERS} iterations of the same solve, reference sources compiled in place "
-                                                      f"(gcc -O3 -march=x86-64-v3), {r['cores']} ranks over a fork+shm mini-MPI"}
+                                                      f"(gcc -O3 {r['march']}), {r['cores']} ranks over a fork+shm mini-MPI"}
             except Exception as exc:        # the GPU numbers must not be lost to a CPU-side hiccup
                 line["cpu_baseline"] = {"value": None, "unit": "iterations/s", "cores": 0, "kind": "reference",
                                         "sample": f"failed: {exc!r}"}
+        if rr is not None:
+            rr.close()
         print(json.dumps(line))
-    dm.destroy()
-    if world > 1:
-        B.comm_finalize()
-        dist.destroy_process_group()
 
 
 def read_traffic(key):

@@ -170,6 +170,9 @@ void  bicg_host_free(void *p);
 
 /* Host-side planning, exposed for CPU-only tests (no CUDA call inside). */
 void bicg_plan_partition(int n, int world, int *counts, int *displs);          /* matrix.c:295-308 */
+/* nnz-balanced contiguous partition (archive/matrix.c:407-420, DYNAMIC_ROWS): used by the loader and the generators when
+ * BICG_PARTITION=nnz; row_nnz[i] = entries of global row i. */
+void bicg_plan_partition_nnz(const unsigned int *row_nnz, int n, int world, int *counts, int *displs);
 /* SpMV tile plan for a CSR block: tiles of <= rows_per_tile rows and <= cap_nnz entries.
  * Writes tile_row[0..ntiles] (first row of each tile); returns ntiles, or -1 if tile_row_cap is too small,
  * or -2 if a single row exceeds cap_nnz. */

@@ -70,6 +70,7 @@ SYMBOLS = {
     "bicg_host_alloc": (C.c_void_p, [C.c_size_t]),
     "bicg_host_free": (None, [C.c_void_p]),
     "bicg_plan_partition": (None, [C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
+    "bicg_plan_partition_nnz": (None, [_P(C.c_uint), C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
     "bicg_plan_tiles": (C.c_int, [_P(C.c_uint), C.c_int, C.c_int, C.c_int, _P(C.c_int), C.c_int]),
     "bicg_plan_cta_tiles": (C.c_int, [_P(C.c_uint), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, _P(C.c_int), C.c_int,
                                       _P(C.c_int), _P(C.c_uint)]),

@@ -96,6 +96,7 @@ void bicg_comm_finalize(void)
     for (auto &kv : c.cache) ms.push_back(kv.second);
     for (bicg_matrix *m : ms) matrix_destroy(m);
     c.cache.clear();
+    c.release_arenas();
     c.rank = 0; c.world = 1; c.allgather = nullptr; c.allgather_ctx = nullptr;
 }
 int bicg_comm_selftest(void)

@@ -96,6 +96,14 @@ struct Context {
     std::multimap<size_t, void *> pool;
     std::map<void *, size_t> live;
     size_t pool_bytes = 0;
+    // IPC-exported arenas (world > 1) are never freed between matrices: an un-cached call (BICG_CACHE=0) re-uses a parked
+    // arena of the same size, and the peers keep their mappings, so no cudaMalloc / cudaIpcOpenMemHandle /
+    // cudaIpcCloseMemHandle sits in the reference-facing call after the first one
+    struct ArenaRec { char *ptr; size_t bytes; unsigned long long id; cudaIpcMemHandle_t handle; };
+    std::multimap<size_t, ArenaRec> arena_pool;
+    std::map<std::pair<int, unsigned long long>, void *> peer_maps;    // (rank, that rank's arena id) -> mapped base
+    unsigned long long next_arena_id = 1;
+    void release_arenas();       // collective: unmap the peers' arenas, free the parked ones
     void host_allgather(const void *send, void *recv, size_t bytes);
 };
 Context &ctx();
@@ -151,6 +159,8 @@ struct bicg_matrix {
     // arena (one cudaMalloc, IPC-shared with the peers)
     char *arena = nullptr;
     size_t arena_bytes = 0;
+    unsigned long long arena_id = 0;         // world > 1: identity of the exported allocation
+    cudaIpcMemHandle_t arena_handle{};
     double *vec_base = nullptr;
     bicg::Scalars *d_sc = nullptr;
     double *d_partials = nullptr;
@@ -174,6 +184,7 @@ struct bicg_matrix {
     int graph_unroll[4] = {};
     // cache key
     const void *host_key = nullptr;
+    uint64_t host_fp = 0;            // content fingerprint of the caller's arrays at upload time (matrix.cu)
     double upload_ms = 0.0;
     uint64_t upload_bytes = 0;
 

@@ -124,10 +124,17 @@ extern "C" int bicg_gen_block(int kind, long long g, double p0, uint64_t seed, i
     if (n > 0x7fffffffLL) return -2;
     RowGen gen{kind, g, p0, seed, n};
 
-    bicg_plan_partition((int)n, world, info->recvcounts, info->displs);
+    std::vector<Entry> row;
+    const char *part = getenv("BICG_PARTITION");
+    if (part && !strcmp(part, "nnz") && world > 1 && kind != 2) {        // kind 2: every row has the same length
+        std::vector<unsigned> row_nnz((size_t)n);
+        for (long long i = 0; i < n; ++i) { gen.row(i, row); row_nnz[(size_t)i] = (unsigned)row.size(); }
+        bicg_plan_partition_nnz(row_nnz.data(), (int)n, world, info->recvcounts, info->displs);     // archive/matrix.c:407-420
+    } else {
+        bicg_plan_partition((int)n, world, info->recvcounts, info->displs);                        // matrix.c:295-308
+    }
     const long long lo = info->displs[rank], nloc = info->recvcounts[rank], hi = lo + nloc;
 
-    std::vector<Entry> row;
     // pass 1: count
     unsigned long long nd = 0, no = 0, ntot_est = 0;
     for (long long i = lo; i < hi; ++i) {

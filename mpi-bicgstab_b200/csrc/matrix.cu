@@ -416,12 +416,54 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::ve
 }
 
 // ------------------------------------------------------------------------------------------------
+// device-side merge of the reference's diag / offd blocks (matrix.c:380-392) into one CSR over [own | ghost] columns
+// ------------------------------------------------------------------------------------------------
+// One thread per row: diag entries first, then offd entries (the reference's accumulation order, matrix.c:437-440);
+// an offd entry's global column becomes ghost_off + ghost slot of the receive run that contains it.
+__global__ void __launch_bounds__(256) merge_rows_kernel(int n_loc, const unsigned *__restrict__ dptr, const unsigned *__restrict__ optr,
+                                                         const double *__restrict__ dval, const unsigned *__restrict__ dcol,
+                                                         const double *__restrict__ oval, const unsigned *__restrict__ ocol,
+                                                         const int *__restrict__ runs /* quadruples */, int nruns, int ghost_off,
+                                                         double *__restrict__ mval, unsigned *__restrict__ mcol)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_loc; i += gridDim.x * blockDim.x) {
+        const unsigned d0 = dptr[i], d1 = dptr[i + 1], o0 = optr[i], o1 = optr[i + 1];
+        unsigned k = d0 + o0;
+        for (unsigned j = d0; j < d1; ++j, ++k) { mval[k] = dval[j]; mcol[k] = dcol[j]; }
+        for (unsigned j = o0; j < o1; ++j, ++k) {
+            const int gc = (int)ocol[j];
+            int a = 0, b = nruns;                          // last run whose first column is <= gc
+            while (b - a > 1) { const int mid = (a + b) >> 1; if (runs[4 * mid] <= gc) a = mid; else b = mid; }
+            mval[k] = oval[j];
+            mcol[k] = (unsigned)(ghost_off + runs[4 * a + 3] + (gc - runs[4 * a]));
+        }
+    }
+}
+
+void Context::release_arenas()
+{
+    if (world > 1 && (!arena_pool.empty() || !peer_maps.empty())) {
+        int token = 0; std::vector<int> all((size_t)world);
+        if (ready) cudaStreamSynchronize(stream);
+        host_allgather(&token, all.data(), sizeof(int));       // every rank is done with every arena
+        for (auto &kv : peer_maps) cudaIpcCloseMemHandle(kv.second);
+        peer_maps.clear();
+        host_allgather(&token, all.data(), sizeof(int));       // nobody still maps what is freed next
+    }
+    for (auto &kv : arena_pool) cudaFree(kv.second.ptr);
+    arena_pool.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
 // matrix creation
 // ------------------------------------------------------------------------------------------------
+constexpr int INLINE_RUNS = 48;      // receive runs that travel inside the bootstrap header (banded matrices: 2 per neighbour)
 struct ArenaHdr {
     cudaIpcMemHandle_t handle;
+    unsigned long long arena_id;
     long long vec_off, vstride, ghost_off, mail_off, hflag_off, msync_off;
-    int n_loc, n_ghost;
+    int n_loc, n_ghost, n_runs, pad_;
+    int runs[4 * INLINE_RUNS];
 };
 
 static double now_ms()
@@ -459,15 +501,15 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     m->host_key = diag->val ? (const void *)diag->val : (const void *)diag;
     m->ghost_off = round_up(m->n_loc, 16);
 
-    // ---- halo plan + merged CSR over [own | ghost] columns (plan.cpp) ------------------------------
+    // ---- halo plan + merged CSR over [own | ghost] columns --------------------------------------------------
+    // The layout (receive runs, ghost slots, merged row pointer) is planned on the host from ptr[] and the offd
+    // columns (plan.cpp); the entries of the two blocks are uploaded as the caller holds them and merged on the
+    // GPU -- no O(nnz) host pass sits in the reference-facing call.
     const unsigned *h_ptr = diag->ptr;
-    const double *h_val = diag->val;
-    const unsigned *h_col = diag->col;
-    std::vector<unsigned> mptr, mcol;
-    std::vector<double> mval;
+    std::vector<unsigned> mptr;
     if (no) {
-        merge_blocks(diag, offd, info, m->rank, m->world, c.cfg.halo_gap, m->ghost_off, mptr, mcol, mval, m->recv_runs, m->n_ghost);
-        h_ptr = mptr.data(); h_val = mval.data(); h_col = mcol.data();
+        plan_merged_layout(diag, offd, info, m->rank, m->world, c.cfg.halo_gap, mptr, m->recv_runs, m->n_ghost);
+        h_ptr = mptr.data();
     }
     m->vstride = (long long)m->ghost_off + round_up(std::max(m->n_ghost, 1), 16);
     unsigned max_row = 0;
@@ -482,12 +524,37 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     BICG_CUDA(cudaMemsetAsync(m->d_ptr + m->n_loc + 1, 0, pad * sizeof(unsigned), c.stream));
     BICG_CUDA(cudaMemsetAsync(m->d_val + m->nnz, 0, pad * sizeof(double), c.stream));
     BICG_CUDA(cudaMemsetAsync(m->d_col + m->nnz, 0, pad * sizeof(unsigned), c.stream));
-    if (m->nnz) {
-        BICG_CUDA(cudaMemcpyAsync(m->d_val, h_val, m->nnz * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-        BICG_CUDA(cudaMemcpyAsync(m->d_col, h_col, m->nnz * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
-    }
     BICG_CUDA(cudaMemcpyAsync(m->d_ptr, h_ptr, ((size_t)m->n_loc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
-    m->upload_bytes = m->nnz * 12 + ((size_t)m->n_loc + 1) * 4;
+    if (!no) {
+        if (nd) {
+            BICG_CUDA(cudaMemcpyAsync(m->d_val, diag->val, nd * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+            BICG_CUDA(cudaMemcpyAsync(m->d_col, diag->col, nd * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+        }
+    } else {
+        const size_t np1 = (size_t)m->n_loc + 1;
+        double *t_dval = (double *)c.dev_alloc(std::max<size_t>(nd, 1) * sizeof(double));
+        double *t_oval = (double *)c.dev_alloc(no * sizeof(double));
+        unsigned *t_dcol = (unsigned *)c.dev_alloc(std::max<size_t>(nd, 1) * sizeof(unsigned));
+        unsigned *t_ocol = (unsigned *)c.dev_alloc(no * sizeof(unsigned));
+        unsigned *t_ptr = (unsigned *)c.dev_alloc(2 * np1 * sizeof(unsigned));
+        int *t_runs = (int *)c.dev_alloc(m->recv_runs.size() * sizeof(int));
+        if (nd) {
+            BICG_CUDA(cudaMemcpyAsync(t_dval, diag->val, nd * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+            BICG_CUDA(cudaMemcpyAsync(t_dcol, diag->col, nd * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+        }
+        BICG_CUDA(cudaMemcpyAsync(t_oval, offd->val, no * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        BICG_CUDA(cudaMemcpyAsync(t_ocol, offd->col, no * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+        BICG_CUDA(cudaMemcpyAsync(t_ptr, diag->ptr, np1 * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+        BICG_CUDA(cudaMemcpyAsync(t_ptr + np1, offd->ptr, np1 * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+        BICG_CUDA(cudaMemcpyAsync(t_runs, m->recv_runs.data(), m->recv_runs.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        const int blocks = std::max(1, std::min((m->n_loc + 255) / 256, c.sm_count * 8));
+        merge_rows_kernel<<<blocks, 256, 0, c.stream>>>(m->n_loc, t_ptr, t_ptr + np1, t_dval, t_dcol, t_oval, t_ocol, t_runs,
+                                                        (int)(m->recv_runs.size() / 4), m->ghost_off, m->d_val, m->d_col);
+        BICG_CUDA(cudaGetLastError());
+        // back to the pool: everything that re-uses these blocks is ordered behind the kernel on the same stream
+        c.dev_free(t_dval); c.dev_free(t_oval); c.dev_free(t_dcol); c.dev_free(t_ocol); c.dev_free(t_ptr); c.dev_free(t_runs);
+    }
+    m->upload_bytes = m->nnz * 12 + ((size_t)m->n_loc + 1) * 4 * (no ? 2 : 1);
 
     lap("merge + alloc + H2D matrix");
     // ---- arena -------------------------------------------------------------------------------------
@@ -503,8 +570,16 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     const size_t msync_off = off; off = align(off + sizeof(MegaSync));
     m->arena_bytes = std::max<size_t>(off, (size_t)4 << 20);     // its own allocation granule: the IPC handle maps exactly this
     if (m->world > 1) {
-        // exported through CUDA IPC: always a fresh allocation of its own (peers map and unmap exactly this one)
-        BICG_CUDA(cudaMalloc((void **)&m->arena, m->arena_bytes));
+        // exported through CUDA IPC: an allocation of its own (peers map exactly this one), parked and re-used by size
+        auto it = c.arena_pool.find(m->arena_bytes);
+        if (it != c.arena_pool.end()) {
+            m->arena = it->second.ptr; m->arena_id = it->second.id; m->arena_handle = it->second.handle;
+            c.arena_pool.erase(it);
+        } else {
+            BICG_CUDA(cudaMalloc((void **)&m->arena, m->arena_bytes));
+            BICG_CUDA(cudaIpcGetMemHandle(&m->arena_handle, m->arena));
+            m->arena_id = c.next_arena_id++;
+        }
     } else {
         m->arena = (char *)c.dev_alloc(m->arena_bytes);
     }
@@ -526,29 +601,46 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     std::vector<std::vector<PushRunHost>> push_host;       // per push slot
     if (m->world > 1) {
         ArenaHdr mine{};
-        BICG_CUDA(cudaIpcGetMemHandle(&mine.handle, m->arena));
+        mine.handle = m->arena_handle; mine.arena_id = m->arena_id;
         mine.vec_off = (long long)vec_off; mine.vstride = m->vstride; mine.ghost_off = m->ghost_off;
         mine.mail_off = (long long)mail_off; mine.hflag_off = (long long)hflag_off; mine.msync_off = (long long)msync_off;
         mine.n_loc = m->n_loc; mine.n_ghost = m->n_ghost;
+        const int my_cnt = (int)(m->recv_runs.size() / 4);
+        mine.n_runs = my_cnt;
+        if (my_cnt <= INLINE_RUNS) std::copy(m->recv_runs.begin(), m->recv_runs.end(), mine.runs);
         std::vector<ArenaHdr> all((size_t)m->world);
-        c.host_allgather(&mine, all.data(), sizeof(ArenaHdr));
+        c.host_allgather(&mine, all.data(), sizeof(ArenaHdr));           // ONE bootstrap round in the common case
         for (int p = 0; p < m->world; ++p) {
             if (p == m->rank) { m->peer_base[p] = m->arena; }
-            else BICG_CUDA(cudaIpcOpenMemHandle(&m->peer_base[p], all[(size_t)p].handle, cudaIpcMemLazyEnablePeerAccess));
+            else {
+                const auto key = std::make_pair(p, all[(size_t)p].arena_id);
+                auto hit = c.peer_maps.find(key);
+                if (hit == c.peer_maps.end()) {
+                    void *base = nullptr;
+                    BICG_CUDA(cudaIpcOpenMemHandle(&base, all[(size_t)p].handle, cudaIpcMemLazyEnablePeerAccess));
+                    hit = c.peer_maps.emplace(key, base).first;
+                }
+                m->peer_base[p] = hit->second;
+            }
             m->peer_vec_off[p] = all[(size_t)p].vec_off; m->peer_vstride[p] = all[(size_t)p].vstride;
             m->peer_ghost_off[p] = all[(size_t)p].ghost_off;
             m->comm.mail[p] = (Mailbox *)((char *)m->peer_base[p] + all[(size_t)p].mail_off);
             m->comm.hflag[p] = (HaloFlag *)((char *)m->peer_base[p] + all[(size_t)p].hflag_off);
             m->peer_msync[p] = (MegaSync *)((char *)m->peer_base[p] + all[(size_t)p].msync_off);
         }
-        // receive lists of every rank (variable length -> two rounds)
-        int my_cnt = (int)(m->recv_runs.size() / 4);
+        // receive lists of every rank: inline in the header, or (irregular matrices with many runs) a second round
         std::vector<int> cnts((size_t)m->world);
-        c.host_allgather(&my_cnt, cnts.data(), sizeof(int));
-        const int max_cnt = std::max(1, *std::max_element(cnts.begin(), cnts.end()));
-        std::vector<int> send((size_t)max_cnt * 4, 0), recv((size_t)max_cnt * 4 * (size_t)m->world);
-        std::copy(m->recv_runs.begin(), m->recv_runs.end(), send.begin());
-        c.host_allgather(send.data(), recv.data(), send.size() * sizeof(int));
+        int max_cnt = 1;
+        for (int p = 0; p < m->world; ++p) { cnts[(size_t)p] = all[(size_t)p].n_runs; max_cnt = std::max(max_cnt, cnts[(size_t)p]); }
+        std::vector<int> recv((size_t)max_cnt * 4 * (size_t)m->world, 0);
+        if (max_cnt <= INLINE_RUNS) {
+            for (int p = 0; p < m->world; ++p)
+                std::copy(all[(size_t)p].runs, all[(size_t)p].runs + 4 * cnts[(size_t)p], recv.begin() + (size_t)p * max_cnt * 4);
+        } else {
+            std::vector<int> send((size_t)max_cnt * 4, 0);
+            std::copy(m->recv_runs.begin(), m->recv_runs.end(), send.begin());
+            c.host_allgather(send.data(), recv.data(), send.size() * sizeof(int));
+        }
 
         unsigned recv_mask = 0, send_mask = 0;
         row_extra.assign((size_t)m->n_loc, 0);
@@ -642,32 +734,65 @@ void matrix_destroy(bicg_matrix *m)
         if (it->second == m) it = c.cache.erase(it); else ++it;
     }
     for (int g = 0; g < 4; ++g) if (m->graph[g]) cudaGraphExecDestroy(m->graph[g]);
-    if (m->world > 1) {
-        int token = 0; std::vector<int> all((size_t)m->world);
-        c.host_allgather(&token, all.data(), sizeof(int));       // peers are done with my arena
-        for (int p = 0; p < m->world; ++p)
-            if (p != m->rank && m->peer_base[p]) cudaIpcCloseMemHandle(m->peer_base[p]);
-        c.host_allgather(&token, all.data(), sizeof(int));
-    }
+    // world > 1: nothing collective here.  The arena is parked, not freed (the peers keep their mappings), and a rank
+    // that has finished its solve has received everything its peers will ever write into this arena: the last
+    // reduction completes only after every rank's last push and post.
     for (int s = 0; s < m->npush; ++s) c.dev_free(m->d_push_runs[s]);
     free_plan(m->plan);
     c.dev_free(m->d_trace);
     c.dev_free(m->mega.d_tile_row); c.dev_free(m->mega.d_tile_nz); c.dev_free(m->mega.d_cta_tile); c.dev_free(m->mega.d_cta_dep);
     c.dev_free(m->d_ghost_first);
     if (m->hist_extra) cudaFree(m->hist_extra);
-    c.dev_free(m->d_val); c.dev_free(m->d_col); c.dev_free(m->d_ptr); c.dev_free(m->arena);
+    c.dev_free(m->d_val); c.dev_free(m->d_col); c.dev_free(m->d_ptr);
+    if (m->world > 1) c.arena_pool.emplace(m->arena_bytes, Context::ArenaRec{m->arena, m->arena_bytes, m->arena_id, m->arena_handle});
+    else c.dev_free(m->arena);
     delete m;
+}
+
+// Content fingerprint of the caller's blocks: sizes + up to 8192 evenly spaced samples of val / col / ptr of both blocks
+// (FNV-1a).  The upload cache is keyed by the host pointer; the fingerprint catches what the pointer cannot -- a
+// different matrix in a recycled allocation, or values changed in place everywhere (diagonal shift, rescaling:
+// csr_shift_diagonal, matrix.c:536-551).  A sparse in-place edit that misses every sample still needs
+// bicg_matrix_invalidate() (or BICG_CACHE=0, which re-reads the caller's arrays on every call like the reference does).
+static uint64_t block_fingerprint(const CSR_Matrix *b, uint64_t h)
+{
+    auto mix = [&](uint64_t v) { h = (h ^ v) * 0x100000001b3ull; };
+    if (!b) { mix(0x9e3779b97f4a7c15ull); return h; }
+    mix(b->nz); mix(b->rows); mix(b->cols);
+    const size_t S = 8192;
+    if (b->nz && b->val && b->col) {
+        const size_t step = std::max<size_t>(1, b->nz / S);
+        for (size_t i = 0; i < b->nz; i += step) {
+            uint64_t bits; memcpy(&bits, &b->val[i], 8);
+            mix(bits); mix(b->col[i]);
+        }
+        uint64_t bits; memcpy(&bits, &b->val[b->nz - 1], 8);
+        mix(bits); mix(b->col[b->nz - 1]);
+    }
+    if (b->ptr) {
+        const size_t np1 = (size_t)b->rows + 1, step = std::max<size_t>(1, np1 / S);
+        for (size_t i = 0; i < np1; i += step) mix(b->ptr[i]);
+        mix(b->ptr[b->rows]);
+    }
+    return h;
+}
+static uint64_t host_fingerprint(const CSR_Matrix *diag, const CSR_Matrix *offd, bool with_offd)
+{
+    uint64_t h = block_fingerprint(diag, 0xcbf29ce484222325ull);
+    return with_offd ? block_fingerprint(offd, h) : h;
 }
 
 bicg_matrix *matrix_get_cached(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, bool *fresh)
 {
     Context &c = ctx();
     const void *key = diag->val ? (const void *)diag->val : (const void *)diag;
+    const uint64_t fp = c.cfg.cache ? host_fingerprint(diag, offd, c.world > 1) : 0;
     if (c.cfg.cache) {
         auto it = c.cache.find(key);
         if (it != c.cache.end()) {
             bicg_matrix *old = it->second;
-            if (old->n_loc == (int)diag->rows && old->n_glob == (int)info->rows && old->nnz == (size_t)diag->nz + (c.world > 1 && offd ? offd->nz : 0)) {
+            if (old->host_fp == fp && old->n_loc == (int)diag->rows && old->n_glob == (int)info->rows &&
+                old->nnz == (size_t)diag->nz + (c.world > 1 && offd ? offd->nz : 0)) {
                 if (fresh) *fresh = false;
                 return old;
             }
@@ -675,6 +800,7 @@ bicg_matrix *matrix_get_cached(const CSR_Matrix *diag, const CSR_Matrix *offd, c
         }
     }
     bicg_matrix *m = matrix_create(diag, offd, info);
+    m->host_fp = fp;
     if (fresh) *fresh = true;
     if (c.cfg.cache) c.cache[key] = m;
     return m;

@@ -113,12 +113,30 @@ extern "C" void MPI_csr_load_matrix_block(char *filename, CSR_Matrix *D, CSR_Mat
 
     info->nz = (unsigned)nz; info->rows = (unsigned)m; info->cols = (unsigned)n;
     memcpy(info->code, code, 4);
-    bicg_plan_partition((int)m, world, info->recvcounts, info->displs);
-    const long long lo = info->displs[me], nloc = info->recvcounts[me], hi = lo + nloc;
-
     const bool pattern = code[2] == 'P', integer = code[2] == 'I';
     const char *ex = getenv("BICG_MM_EXPAND_SYMMETRIC");
     const bool expand = ex && atoi(ex) && code[3] == 'S';
+
+    // Partition: the reference's equal-rows rule (matrix.c:295-308), or -- BICG_PARTITION=nnz -- its archived nnz-balanced
+    // rule (archive/matrix.c:407-420), which needs the row lengths of the whole file first: one extra counting pass
+    // over the mapped text (still far cheaper than the reference's two fscanf passes).
+    const char *part = getenv("BICG_PARTITION");
+    if (part && !strcmp(part, "nnz") && world > 1) {
+        std::vector<unsigned> row_nnz((size_t)m, 0u);
+        Cursor c2 = c;
+        for (long long e = 0; e < nz; ++e) {
+            long long r, cc;
+            if (!c2.number(r) || !c2.number(cc)) fail("ERROR: reading matrix data.");
+            if (!pattern) { double v; long long iv; if (integer ? !c2.number(iv) : !c2.number(v)) fail("ERROR: reading matrix data."); }
+            if (r < 1 || r > m || cc < 1 || cc > n) fail("ERROR: reading matrix data.");
+            ++row_nnz[(size_t)(r - 1)];
+            if (expand && r != cc) ++row_nnz[(size_t)(cc - 1)];
+        }
+        bicg_plan_partition_nnz(row_nnz.data(), (int)m, world, info->recvcounts, info->displs);
+    } else {
+        bicg_plan_partition((int)m, world, info->recvcounts, info->displs);
+    }
+    const long long lo = info->displs[me], nloc = info->recvcounts[me], hi = lo + nloc;
 
     struct Ent { unsigned row; unsigned col; double val; };
     std::vector<Ent> dent, oent;

@@ -17,6 +17,30 @@ extern "C" void bicg_plan_partition(int n, int world, int *counts, int *displs)
     }
 }
 
+// nnz-balanced variant (the reference's archived DYNAMIC_ROWS option, archive/matrix.c:407-420): ranks take consecutive
+// rows until their entry count reaches nnz / world; the last rank takes the rest.  Contiguous blocks, so everything
+// downstream (diag / offd split, halo plan, recvcounts / displs) is unchanged.
+extern "C" void bicg_plan_partition_nnz(const unsigned int *row_nnz, int n, int world, int *counts, int *displs)
+{
+    unsigned long long total = 0;
+    for (int i = 0; i < n; ++i) total += row_nnz[i];
+    const unsigned long long target = total / (unsigned long long)world;
+    int start = 0;
+    for (int p = 0; p < world; ++p) {
+        int end = n;
+        if (p < world - 1) {
+            unsigned long long cum = 0;
+            for (int i = start; i < n; ++i) {
+                cum += row_nnz[i];
+                if (cum >= target) { end = i + 1; break; }
+            }
+        }
+        counts[p] = end - start;
+        displs[p] = start;
+        start = end;
+    }
+}
+
 namespace bicg {
 
 // Greedy tiling: a tile closes when adding the next row would exceed rows_per_tile rows or cap_nnz
@@ -99,6 +123,24 @@ void merge_blocks(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Mat
             }
         mptr[(size_t)i + 1] = (unsigned)k;
     }
+}
+
+// The layout half of merge_blocks without touching the entries: receive list (quadruples first_col, len, owner,
+// ghost_idx), number of ghost slots and the merged row pointer mptr[i] = diag->ptr[i] + offd->ptr[i].  The entries
+// themselves are merged on the GPU (matrix.cu: merge_rows_kernel) from the two blocks uploaded as they are.
+void plan_merged_layout(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, int self, int world, int gap,
+                        std::vector<unsigned> &mptr, std::vector<int> &recv, int &n_ghost)
+{
+    std::vector<HaloRun> runs;
+    const bool far = offd && offd->nz > 0 && world > 1;
+    if (far) plan_halo_runs(offd, info, world, gap, self, runs);
+    recv.clear();
+    int ghost = 0;
+    for (const HaloRun &r : runs) { recv.insert(recv.end(), {r.first, r.len, r.owner, ghost}); ghost += r.len; }
+    n_ghost = ghost;
+    const int n_loc = (int)diag->rows;
+    mptr.resize((size_t)n_loc + 1);
+    for (int i = 0; i <= n_loc; ++i) mptr[(size_t)i] = diag->ptr[i] + (far ? offd->ptr[i] : 0u);
 }
 
 // Tile plan of the persistent solver kernel (mega.cu).  CTA g of `ctas` owns a contiguous row range; the ranges are

@@ -17,6 +17,8 @@ void plan_halo_runs(const CSR_Matrix *offd, const INFO_Matrix *info, int world, 
 void merge_blocks(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, int self, int world, int gap,
                   int ghost_off, std::vector<unsigned> &mptr, std::vector<unsigned> &mcol, std::vector<double> &mval,
                   std::vector<int> &recv, int &n_ghost);
+void plan_merged_layout(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, int self, int world, int gap,
+                        std::vector<unsigned> &mptr, std::vector<int> &recv, int &n_ghost);
 void plan_push_runs(const int *all_recv, const int *cnts, int stride, int self, int dest, int my_first,
                     std::vector<PushRunHost> &out);
 

@@ -21,3 +21,32 @@ def global_csr(B, kind, g, p0, seed=12345):
 def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+_BIG = {}
+
+
+def big_csr(kind, g, p0, tmpdir="/dev/shm"):
+    """Full-size synthetic matrix as (file, n, ptr, col, val): written once per session by the stand-alone generator
+    oracle/gen_csr (binary layout of oracle.py: write_csr_bin), so neither numpy index gymnastics nor a second copy of the
+    1.6 M-row matrix is needed.  The file is what oracle/_ref/ref_driver_* reads."""
+    import os, subprocess, tempfile
+    key = (kind, g, p0)
+    if key not in _BIG:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        gen = os.path.join(root, "oracle", "gen_csr")
+        if not os.path.exists(gen):
+            subprocess.run(["make", "-C", os.path.join(root, "oracle"), "oracle"], check=True)
+        d = tempfile.mkdtemp(dir=tmpdir if os.path.isdir(tmpdir) else None)
+        f = os.path.join(d, f"{kind}_{g}.bin")
+        kinds = {"stencil15": 0, "laplace5": 1, "random": 2, "convdiff": 3}
+        subprocess.run([gen, str(kinds[kind]), str(int(g)), repr(float(p0)), f], check=True, capture_output=True)
+        with open(f, "rb") as fh:
+            n, nnz = (int(v) for v in np.fromfile(fh, dtype=np.int64, count=2))
+            ptr = np.fromfile(fh, dtype=np.uint32, count=n + 1)
+            col = np.fromfile(fh, dtype=np.uint32, count=nnz)
+            if (n + 1 + nnz) % 2:
+                np.fromfile(fh, dtype=np.uint32, count=1)
+            val = np.fromfile(fh, dtype=np.float64, count=nnz)
+        _BIG[key] = (f, n, ptr, col, val)
+    return _BIG[key]

@@ -214,3 +214,54 @@ def test_persistent_kernel_tile_plan(B, rows, ctas, rpt, extra):
         h = np.diff(t[c[g]:c[g + 1] + 1])
         assert h.size == 0 or h.max() - h.min() <= 1
     assert mx.value == (ptr[t[1:]].astype(np.int64) - ptr[t[:-1]].astype(np.int64)).max()
+
+
+@pytest.mark.parametrize("n,world", [(1000, 4), (17, 3), (5, 8), (100000, 8)])
+def test_nnz_balanced_partition_rule(B, n, world):
+    """bicg_plan_partition_nnz = the reference's archived DYNAMIC_ROWS rule (archive/matrix.c:407-420): ranks take rows
+    until their entry count reaches nnz / world, the last rank takes the rest."""
+    rng = np.random.default_rng(n + world)
+    row_nnz = rng.integers(1, 40, size=n).astype(np.uint32)
+    row_nnz[: n // 5] *= 6                                   # a dense head: equal-rows would be badly unbalanced
+    cnt = (C.c_int * world)(); dsp = (C.c_int * world)()
+    B.lib.bicg_plan_partition_nnz(row_nnz.ctypes.data_as(C.POINTER(C.c_uint)), n, world, cnt, dsp)
+    cnt, dsp = np.array(cnt[:]), np.array(dsp[:])
+    assert cnt.sum() == n and dsp[0] == 0 and np.all(dsp[1:] == np.cumsum(cnt)[:-1]) and np.all(cnt >= 0)
+    target = int(row_nnz.sum()) // world                    # restatement of the archived loop
+    start = 0
+    for p in range(world):
+        end = n
+        if p < world - 1:
+            cum = 0
+            for i in range(start, n):
+                cum += int(row_nnz[i])
+                if cum >= target:
+                    end = i + 1
+                    break
+        assert (dsp[p], cnt[p]) == (start, end - start)
+        start = end
+    if n >= 1000:                                            # and it does balance the entries
+        per = np.add.reduceat(row_nnz.astype(np.int64), dsp[cnt > 0])
+        assert per.max() <= 1.15 * row_nnz.sum() / world + row_nnz.max()
+
+
+def test_generator_and_loader_honour_nnz_partition(B, tmp_path, monkeypatch):
+    monkeypatch.setenv("BICG_PARTITION", "nnz")
+    world = 3
+    blocks = [B.gen_block("stencil15", 9, 14.0, rank=r, world=world) for r in range(world)]
+    monkeypatch.delenv("BICG_PARTITION")
+    full = B.gen_block("stencil15", 9, 14.0)
+    ptr, col, val = B.block_to_global_csr(full)
+    row_nnz = np.diff(ptr).astype(np.uint32)
+    cnt = (C.c_int * world)(); dsp = (C.c_int * world)()
+    B.lib.bicg_plan_partition_nnz(row_nnz.ctypes.data_as(C.POINTER(C.c_uint)), full.n, world, cnt, dsp)
+    for r, blk in enumerate(blocks):
+        assert list(blk.recvcounts) == list(cnt[:]) and list(blk.displs) == list(dsp[:])
+        p2, c2, v2 = B.block_to_global_csr(blk, rank=r)
+        lo, hi = dsp[r], dsp[r] + cnt[r]
+        # same rows as the global matrix (entries of a row: diag block first, then offd -- compare as sets per row)
+        assert np.array_equal(np.diff(p2), np.diff(ptr[lo:hi + 1]))
+        for i in (0, cnt[r] // 2, cnt[r] - 1):
+            a = sorted(zip(c2[p2[i]:p2[i + 1]], v2[p2[i]:p2[i + 1]]))
+            b = sorted(zip(col[ptr[lo + i]:ptr[lo + i + 1]], val[ptr[lo + i]:ptr[lo + i + 1]]))
+            assert a == b

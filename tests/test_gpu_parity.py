@@ -10,7 +10,7 @@ reduction), so bit-exactness is not expected beyond the element-wise updates.
 import numpy as np
 import pytest
 
-from helpers import METHODS, RR, SMALL_CASES, global_csr, rel_err
+from helpers import METHODS, RR, SMALL_CASES, big_csr, global_csr, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -218,3 +218,58 @@ def test_reference_main_c_runs_on_the_library(B, O, tmp_path):
         assert abs(it - ref["iters"]) <= 2, (method, it, ref["iters"])
         assert re.search(r"Iteration: 10, Residual: \d\.\d{6}e[-+]\d\d", out)
         assert float(re.search(r"Final r\s*:\s*(\S+)", out).group(1)) <= 1e-10
+
+
+_REF_ITERS = {}
+
+
+def test_bench_matrix_parity(B, O):
+    """The BASELINE config-2 matrix itself (T' surrogate with the bench's p0 = 14: 1,601,613 rows, 23,616,325 entries),
+    tol 1e-8: H-level against the oracle, C-level against the reference's own sources compiled in place
+    (oracle/_ref/ref_driver_strict, P = 1; about 45 s of CPU, run once per session)."""
+    f, n, ptr, col, val = big_csr("stencil15", 117, 14.0)
+    blk = B.gen_block("stencil15", 117, 14.0)
+    assert blk.n == n and blk.nnz_loc == val.size
+    b_ref = O.spmv(n, ptr, col, val, np.ones(n))
+    dm = B.DeviceMatrix(blk)
+    b = dm.spmv(np.ones(n))
+    assert rel_err(b, b_ref) <= 1e-13
+    B.set_options(tol=1e-8, max_iter=1000)
+    x = np.zeros(n)
+    r = b.copy()
+    it, st = dm.solve("bicgstab", x, r)
+    hist = B.last_history()
+    assert st["converged"] == 1
+    ref10 = O.solve("bicgstab", n, ptr, col, val, b_ref, tol=1e-8, max_iter=10)
+    got, want = np.sqrt(hist[1:11]), np.sqrt(ref10["hist"][1:11])
+    assert np.all(np.abs(got - want) <= 1e-10 * want + H_FLOOR), np.abs(got - want) / want
+    if O.have_ref("ref_driver_strict"):
+        if "bicgstab" not in _REF_ITERS:
+            _REF_ITERS["bicgstab"] = O.ref_driver("bicgstab", f, P=1, rhs="a1", tol=1e-8, max_iter=1000, flavour="strict",
+                                                  want_vectors=False, timeout=1200)["iters"]
+        ref_it = _REF_ITERS["bicgstab"]
+        assert abs(it - ref_it) <= max(2, int(0.02 * ref_it)), (it, ref_it)
+    true_res = np.linalg.norm(b_ref - O.spmv(n, ptr, col, val, x)) / np.linalg.norm(b_ref)
+    assert true_res <= 1e-7 and np.abs(x - 1.0).max() <= 1e-5
+    dm.destroy()
+
+
+def test_random_block_parity(B, O):
+    """A >= 1 M-row block of the config-5 family (random, 32 entries per row, CA-BiCGStab): the long-row path of the
+    persistent kernel (LANES > 1) at size."""
+    f, n, ptr, col, val = big_csr("random", 1_000_003, 32)
+    blk = B.gen_block("random", 1_000_003, 32)
+    b_ref = O.spmv(n, ptr, col, val, np.ones(n))
+    dm = B.DeviceMatrix(blk)
+    B.set_options(tol=1e-10, max_iter=200)
+    x = np.zeros(n)
+    r = dm.spmv(np.ones(n))
+    assert rel_err(r, b_ref) <= 1e-13
+    it, st = dm.solve("ca_bicgstab", x, r)
+    hist = B.last_history()
+    ref = O.solve("ca_bicgstab", n, ptr, col, val, b_ref, tol=1e-10, max_iter=200)
+    m = min(10, it, ref["iters"])
+    got, want = np.sqrt(hist[1:m + 1]), np.sqrt(ref["hist"][1:m + 1])
+    assert np.all(np.abs(got - want) <= 1e-10 * want + H_FLOOR), np.abs(got - want) / want
+    assert abs(it - ref["iters"]) <= 2 and np.abs(x - 1.0).max() <= 1e-8
+    dm.destroy()
