@@ -184,6 +184,11 @@ int  bicg_plan_tiles(const unsigned int *ptr, int rows, int rows_per_tile, int c
  * cta_tile[0..ctas] (first tile of each CTA).  Returns ntiles (or -needed ints), *max_tile_nnz = entries of the fullest tile. */
 int  bicg_plan_cta_tiles(const unsigned int *ptr, int rows, int ctas, int rows_per_tile, const unsigned char *row_extra,
                          int extra_weight, int *tile_row, int tile_row_cap, int *cta_tile, unsigned int *max_tile_nnz);
+/* The same with a stage capacity: tiles hold <= cap_limit entries; a row longer than cap_limit becomes a run of chunk tiles
+ * (tile_flag 1 = more chunks of the row follow, 2 = last chunk, 0 = ordinary tile of whole rows); tile_nz[t] = first entry of
+ * tile t.  The three tile arrays need tile_cap ints each. */
+int  bicg_plan_cta_tiles_capped(const unsigned int *ptr, int rows, int ctas, int rows_per_tile, int cap_limit, int *tile_row,
+                                unsigned int *tile_nz, int *tile_flag, int tile_cap, int *cta_tile, unsigned int *max_tile_nnz);
 /* Halo plan of rank `self`: which global columns of the offd block it must receive, as merged runs.
  * runs_out holds triples (first_col, length, owner); returns the number of runs (or -needed if cap is small).
  * gap: runs of one owner separated by <= gap unreferenced columns are merged. */

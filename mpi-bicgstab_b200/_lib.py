@@ -74,6 +74,8 @@ SYMBOLS = {
     "bicg_plan_tiles": (C.c_int, [_P(C.c_uint), C.c_int, C.c_int, C.c_int, _P(C.c_int), C.c_int]),
     "bicg_plan_cta_tiles": (C.c_int, [_P(C.c_uint), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, _P(C.c_int), C.c_int,
                                       _P(C.c_int), _P(C.c_uint)]),
+    "bicg_plan_cta_tiles_capped": (C.c_int, [_P(C.c_uint), C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_uint), _P(C.c_int),
+                                             C.c_int, _P(C.c_int), _P(C.c_uint)]),
     "bicg_plan_halo_runs": (C.c_int, [_P(CSR_Matrix), _P(INFO_Matrix), C.c_int, C.c_int, C.c_int, _P(C.c_int), C.c_int]),
     "bicg_plan_merge": (C.c_longlong, [_P(CSR_Matrix), _P(CSR_Matrix), _P(INFO_Matrix), C.c_int, C.c_int, C.c_int, C.c_int,
                                        _P(C.c_uint), _P(C.c_uint), _P(C.c_double), _P(C.c_int), C.c_int, _P(C.c_int)]),

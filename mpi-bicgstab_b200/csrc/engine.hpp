@@ -129,6 +129,8 @@ struct MegaPlan {
     unsigned *d_tile_nz = nullptr;
     int *d_cta_tile = nullptr;
     int4 *d_cta_dep = nullptr;
+    int *d_tile_flag = nullptr;  // only when rows longer than a stage were cut into chunk tiles
+    bool chunked = false;
     std::vector<int> cta_row;    // grid + 1: first row of every CTA
 };
 

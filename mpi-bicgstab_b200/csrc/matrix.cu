@@ -383,15 +383,20 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::ve
         if (c.cfg.mega_threads && c.cfg.mega_threads != threads) continue;
         if (!mega_has_variant(threads, lanes)) continue;
         const int rpt = threads / lanes;
-        std::vector<int> tile_row, cta_tile;
+        std::vector<int> tile_row, cta_tile, tile_flag;
+        std::vector<unsigned> tile_nz;
+        // a stage must hold one tile; at least two stages must fit.  Tiles (or single rows) with more entries than that
+        // are cut by the planner: greedy tiles + chunked long rows (plan.cpp)
+        const int cap_limit = (int)(((SMEM_MAX / 2 - (long long)(rpt + 8) * 4) / 12 - 8) / 32 * 32);
         const unsigned max_tile_nnz = plan_cta_tiles(h_ptr, m->n_loc, G, rpt, row_extra.empty() ? nullptr : row_extra.data(),
-                                                     c.cfg.boundary_weight, tile_row, cta_tile);
+                                                     c.cfg.boundary_weight, tile_row, cta_tile, cap_limit, &tile_nz, &tile_flag);
         const int cap = round_up((long long)max_tile_nnz + 8, 32);
         const long long stage = (long long)cap * 12 + (long long)(rpt + 8) * 4;
         int stages = (int)std::min<long long>(4, SMEM_MAX / stage);
-        if (stages < 2) continue;                       // rows too long for this tile height
-        std::vector<unsigned> tile_nz(tile_row.size());
-        for (size_t i = 0; i < tile_row.size(); ++i) tile_nz[i] = h_ptr[tile_row[i]];
+        if (stages < 2) continue;                       // cannot happen with the cap-limited plan; kept as a guard
+        bool chunked = false;
+        for (int f : tile_flag) chunked = chunked || f != 0;
+        mp.chunked = chunked;
         mp.threads = threads; mp.lanes = lanes; mp.stages = stages; mp.cap = cap; mp.grid = G;
         mp.smem = mega_smem_bytes(cap, stages, threads, lanes);
         mp.ntiles = (int)tile_row.size() - 1;
@@ -401,6 +406,11 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::ve
         mp.d_tile_nz = (decltype(mp.d_tile_nz))c.dev_alloc(tile_nz.size() * sizeof(unsigned));
         mp.d_cta_tile = (decltype(mp.d_cta_tile))c.dev_alloc(cta_tile.size() * sizeof(int));
         mp.d_cta_dep = (decltype(mp.d_cta_dep))c.dev_alloc((size_t)G * sizeof(int4));
+        mp.d_tile_flag = nullptr;
+        if (chunked) {
+            mp.d_tile_flag = (int *)c.dev_alloc(tile_flag.size() * sizeof(int));
+            BICG_CUDA(cudaMemcpyAsync(mp.d_tile_flag, tile_flag.data(), tile_flag.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        }
         BICG_CUDA(cudaMemcpyAsync(mp.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
         BICG_CUDA(cudaMemcpyAsync(mp.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
         BICG_CUDA(cudaMemcpyAsync(mp.d_cta_tile, cta_tile.data(), cta_tile.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
@@ -741,6 +751,7 @@ void matrix_destroy(bicg_matrix *m)
     free_plan(m->plan);
     c.dev_free(m->d_trace);
     c.dev_free(m->mega.d_tile_row); c.dev_free(m->mega.d_tile_nz); c.dev_free(m->mega.d_cta_tile); c.dev_free(m->mega.d_cta_dep);
+    c.dev_free(m->mega.d_tile_flag);
     c.dev_free(m->d_ghost_first);
     if (m->hist_extra) cudaFree(m->hist_extra);
     c.dev_free(m->d_val); c.dev_free(m->d_col); c.dev_free(m->d_ptr);

@@ -37,7 +37,7 @@ namespace {
 constexpr int PROW_PAD = 8;
 constexpr int RED_THREADS = MEGA_MAX_CTAS;          // one polled slot per thread
 constexpr int RED_WARPS = RED_THREADS / 32;
-struct StageHdr { int row0, row1; unsigned a0; int rowa; };
+struct StageHdr { int row0, row1; unsigned a0; int rowa; unsigned lo, hi; int flag; int pad_; };   // lo, hi: the tile's entries relative to a0
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar)
 {
@@ -343,6 +343,7 @@ struct Mega {
     {
         const int stages = a.stages, cap = a.cap;
         const int sub = tid % LANES, row_in_tile = tid / LANES;
+        double carry = 0.0;
         for (int lt = 0; lt < my_tiles; ++lt, ++vis) {
             const int s = (int)(vis % (unsigned)stages);
             mbar_wait(smem_u32(&sh.full_bar[s]), (vis / (unsigned)stages) & 1u);
@@ -351,6 +352,44 @@ struct Mega {
             const unsigned *scol = reinterpret_cast<const unsigned *>(sval + cap);
             const unsigned *sptr = scol + cap;
             const StageHdr h = sh.hdr[s];
+            if (h.flag != 0) {
+                // one chunk of a row longer than a stage: the whole CTA multiplies it, the row's partial sum is carried
+                // from chunk to chunk in `carry` (same value in every thread) and the row is finished by its last chunk
+                double part[1] = {0.0};
+                for (unsigned jj = h.lo + (unsigned)tid; jj < h.hi; jj += 4u * CT) {
+                    double pv[4], px[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const unsigned idx = min(jj + (unsigned)(u * CT), h.hi - 1u);
+                        pv[u] = sval[idx]; px[u] = ld_coherent(x + scol[idx]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (jj + (unsigned)(u * CT) < h.hi) part[0] = fma(pv[u], px[u], part[0]);
+                }
+                cblock_sum<1, CT>(part, sh.scratch);                   // fixed order; result in every lane of warp 0
+                if (tid == 0) sh.red[0][0] = part[0];
+                nbar(1, CT);
+                carry += sh.red[0][0];
+                if (h.flag == 2) {
+                    if (tid == 0) {
+                        const int row = h.row0;
+                        const double acc = carry;
+                        y[row] = acc;
+                        if (EPI == EPI_RH_Y) dot[0] = fma(a.v.rh[row], acc, dot[0]);
+                        if (EPI == EPI_QY_YY) { dot[0] = fma(a.v.r[row], acc, dot[0]); dot[1] = fma(acc, acc, dot[1]); }
+                        if (EPI == EPI_CA4) {
+                            const double rh = a.v.rh[row];
+                            dot[0] = fma(rh, a.v.r[row], dot[0]); dot[1] = fma(rh, acc, dot[1]);
+                            dot[2] = fma(rh, a.v.s[row], dot[2]); dot[3] = fma(rh, a.v.z[row], dot[3]);
+                        }
+                    }
+                    carry = 0.0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sh.empty_bar[s]));
+                continue;
+            }
             const int row = h.row0 + row_in_tile;
             const bool valid = row < h.row1;
             int j = 0, e = 0;
@@ -595,7 +634,7 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
                 double   *sval = reinterpret_cast<double *>(st);
                 unsigned *scol = reinterpret_cast<unsigned *>(sval + cap);
                 unsigned *sptr = scol + cap;
-                sh.hdr[s] = StageHdr{row0, row1, a0, rowa};
+                sh.hdr[s] = StageHdr{row0, row1, a0, rowa, p0 - a0, p1 - a0, a.tile_flag ? a.tile_flag[t] : 0, 0};
                 const unsigned bar = smem_u32(&sh.full_bar[s]);
                 mbar_arrive_expect_tx(bar, cnt * 12u + (unsigned)cntp * 4u);
                 if (cnt) {

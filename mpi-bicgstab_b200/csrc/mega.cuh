@@ -59,6 +59,7 @@ struct MegaArgs {
     const int      *tile_row;   // ntiles + 1
     const unsigned *tile_nz;    // ntiles + 1
     const int      *cta_tile;   // grid + 1 : first tile of every CTA (contiguous ownership)
+    const int      *tile_flag;  // null, or per tile: 0 whole rows, 1 / 2 chunk of ONE long row (more follow / last)
     int cap, stages;
     int ghost_off;
     int l2_hint;                // 1: matrix stream is loaded with an L2 evict-first policy

@@ -151,9 +151,12 @@ void plan_merged_layout(const CSR_Matrix *diag, const CSR_Matrix *offd, const IN
 // equal height.  tile_row gets the first row of every tile plus a final `rows`; cta_tile[g] is the index of CTA g's
 // first tile (cta_tile[ctas] = #tiles).  Returns the largest number of entries in any tile.
 unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int rows_per_tile, const unsigned char *row_extra,
-                        int extra_weight, std::vector<int> &tile_row, std::vector<int> &cta_tile)
+                        int extra_weight, std::vector<int> &tile_row, std::vector<int> &cta_tile, int cap_limit,
+                        std::vector<unsigned> *tile_nz, std::vector<int> *tile_flag)
 {
     tile_row.clear();
+    if (tile_nz) tile_nz->clear();
+    if (tile_flag) tile_flag->clear();
     cta_tile.assign((size_t)ctas + 1, 0);
     std::vector<int> first((size_t)ctas + 1, rows);
     first[0] = 0;
@@ -174,6 +177,7 @@ unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int rows_per_ti
             first[(size_t)g] = cut;
         }
     }
+    // pass 1: equal-height tiles (what regular matrices get)
     unsigned max_tile_nnz = 0;
     for (int g = 0; g < ctas; ++g) {
         const int lo = first[(size_t)g], hi = first[(size_t)g + 1];
@@ -188,6 +192,42 @@ unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int rows_per_ti
     }
     cta_tile[(size_t)ctas] = (int)tile_row.size();
     tile_row.push_back(rows);
+    if (cap_limit <= 0 || max_tile_nnz <= (unsigned)cap_limit || !tile_nz || !tile_flag) {
+        if (tile_nz) { tile_nz->resize(tile_row.size()); for (size_t i = 0; i < tile_row.size(); ++i) (*tile_nz)[i] = ptr[tile_row[i]]; }
+        if (tile_flag) tile_flag->assign(tile_row.size(), 0);
+        return max_tile_nnz;
+    }
+    // pass 2 (irregular matrices): some tile does not fit a shared-memory stage.  Greedy tiles of <= rows_per_tile rows
+    // and <= cap_limit entries; a row longer than cap_limit becomes a run of CHUNK tiles (flag 1: more chunks of this
+    // row follow, flag 2: last chunk) that the whole CTA multiplies cooperatively, carrying the row's partial sum from
+    // chunk to chunk (mega.cu).  tile_nz then holds the first ENTRY of every tile (rows alone no longer determine it).
+    tile_row.clear(); tile_nz->clear(); tile_flag->clear();
+    max_tile_nnz = 0;
+    for (int g = 0; g < ctas; ++g) {
+        const int lo = first[(size_t)g], hi = first[(size_t)g + 1];
+        cta_tile[(size_t)g] = (int)tile_row.size();
+        int r0 = lo;
+        while (r0 < hi) {
+            const unsigned base = ptr[r0];
+            const unsigned len0 = ptr[r0 + 1] - base;
+            if (len0 > (unsigned)cap_limit) {
+                for (unsigned off = 0; off < len0; off += (unsigned)cap_limit) {
+                    tile_row.push_back(r0); tile_nz->push_back(base + off);
+                    tile_flag->push_back(off + (unsigned)cap_limit < len0 ? 1 : 2);
+                    max_tile_nnz = std::max(max_tile_nnz, std::min<unsigned>((unsigned)cap_limit, len0 - off));
+                }
+                ++r0;
+                continue;
+            }
+            int r1 = r0;
+            while (r1 < hi && r1 - r0 < rows_per_tile && ptr[r1 + 1] - base <= (unsigned)cap_limit) ++r1;
+            tile_row.push_back(r0); tile_nz->push_back(base); tile_flag->push_back(0);
+            max_tile_nnz = std::max(max_tile_nnz, ptr[r1] - base);
+            r0 = r1;
+        }
+    }
+    cta_tile[(size_t)ctas] = (int)tile_row.size();
+    tile_row.push_back(rows); tile_nz->push_back(ptr[rows]); tile_flag->push_back(0);
     return max_tile_nnz;
 }
 
@@ -236,9 +276,26 @@ extern "C" int bicg_plan_cta_tiles(const unsigned int *ptr, int rows, int ctas, 
                                    int extra_weight, int *tile_row, int tile_row_cap, int *cta_tile, unsigned int *max_tile_nnz)
 {
     std::vector<int> tr, ct;
-    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, rows_per_tile, row_extra, extra_weight, tr, ct);
+    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, rows_per_tile, row_extra, extra_weight, tr, ct, 0, nullptr, nullptr);
     if ((int)tr.size() > tile_row_cap) return -(int)tr.size();
     std::memcpy(tile_row, tr.data(), tr.size() * sizeof(int));
+    std::memcpy(cta_tile, ct.data(), ct.size() * sizeof(int));
+    if (max_tile_nnz) *max_tile_nnz = mx;
+    return (int)tr.size() - 1;
+}
+
+// cap-limited variant: tiles of <= cap_limit entries; rows longer than that become chunk tiles (tile_flag 1 / 2).  tile_nz[t] is
+// the first entry of tile t.  All three arrays need room for tile_cap ints; returns ntiles or -needed.
+extern "C" int bicg_plan_cta_tiles_capped(const unsigned int *ptr, int rows, int ctas, int rows_per_tile, int cap_limit, int *tile_row,
+                                          unsigned int *tile_nz, int *tile_flag, int tile_cap, int *cta_tile, unsigned int *max_tile_nnz)
+{
+    std::vector<int> tr, ct, fl;
+    std::vector<unsigned> nz;
+    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, rows_per_tile, nullptr, 0, tr, ct, cap_limit, &nz, &fl);
+    if ((int)tr.size() > tile_cap) return -(int)tr.size();
+    std::memcpy(tile_row, tr.data(), tr.size() * sizeof(int));
+    std::memcpy(tile_nz, nz.data(), nz.size() * sizeof(unsigned));
+    std::memcpy(tile_flag, fl.data(), fl.size() * sizeof(int));
     std::memcpy(cta_tile, ct.data(), ct.size() * sizeof(int));
     if (max_tile_nnz) *max_tile_nnz = mx;
     return (int)tr.size() - 1;

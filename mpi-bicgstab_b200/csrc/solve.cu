@@ -90,6 +90,7 @@ struct Seq {
         a.ghost_first = m->d_ghost_first; a.cta_dep = m->mega.d_cta_dep;
         a.val = m->d_val; a.col = m->d_col; a.ptr = m->d_ptr;
         a.tile_row = m->mega.d_tile_row; a.tile_nz = m->mega.d_tile_nz; a.cta_tile = m->mega.d_cta_tile;
+        a.tile_flag = m->mega.d_tile_flag;
         a.cap = m->mega.cap; a.stages = m->mega.stages;
         a.ghost_off = m->ghost_off; a.l2_hint = c.cfg.l2_hint;
         a.vec_base = m->vec_base; a.vstride = m->vstride;

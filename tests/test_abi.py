@@ -265,3 +265,33 @@ def test_generator_and_loader_honour_nnz_partition(B, tmp_path, monkeypatch):
             a = sorted(zip(c2[p2[i]:p2[i + 1]], v2[p2[i]:p2[i + 1]]))
             b = sorted(zip(col[ptr[lo + i]:ptr[lo + i + 1]], val[ptr[lo + i]:ptr[lo + i + 1]]))
             assert a == b
+
+
+def test_persistent_kernel_plan_cuts_long_rows_into_chunks(B):
+    """Cap-limited plan (plan.cpp): tiles hold <= cap entries; a longer row becomes consecutive chunk tiles (flag 1 ... 1 2)
+    inside ONE CTA's range; every entry of the matrix is covered exactly once, in order."""
+    rng = np.random.default_rng(5)
+    rows, ctas, rpt, cap = 6000, 148, 512, 1000
+    lens = rng.integers(0, 12, size=rows)
+    lens[[0, 17, 2999, 5999]] = [4096, 1000, 1001, 2500]          # 1000 fits exactly, the others are cut
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    tc = rows + ctas + 64
+    tr = (C.c_int * tc)(); nz = (C.c_uint * tc)(); fl = (C.c_int * tc)(); ct = (C.c_int * (ctas + 1))(); mx = C.c_uint()
+    nt = B.lib.bicg_plan_cta_tiles_capped(ptr.ctypes.data_as(C.POINTER(C.c_uint)), rows, ctas, rpt, cap, tr, nz, fl, tc, ct, C.byref(mx))
+    assert nt > 0 and mx.value <= cap
+    t, z, f, c = np.array(tr[:nt + 1]), np.array(nz[:nt + 1]), np.array(fl[:nt + 1]), np.array(ct[:])
+    assert t[0] == 0 and t[-1] == rows and z[0] == 0 and z[-1] == ptr[-1]
+    assert np.all(np.diff(z.astype(np.int64)) >= 0) and np.all(np.diff(z.astype(np.int64)) <= cap)      # contiguous cover of the entries
+    for k in range(nt):
+        if f[k] == 0:
+            assert t[k + 1] > t[k] or z[k + 1] == z[k]
+            assert z[k] == ptr[t[k]] and z[k + 1] == ptr[t[k + 1]] and t[k + 1] - t[k] <= rpt
+        else:
+            r = t[k]
+            assert lens[r] > cap and ptr[r] <= z[k] < ptr[r + 1]
+            assert (f[k] == 2) == (z[k + 1] == ptr[r + 1]) and t[k + 1] == (r + 1 if f[k] == 2 else r)
+    chunk_rows = set(t[:-1][f[:-1] != 0])
+    assert chunk_rows == {0, 2999, 5999}
+    for g in range(ctas):                                         # a row's chunks never straddle two CTAs
+        if c[g] < nt and c[g] > 0:
+            assert f[c[g] - 1] != 1

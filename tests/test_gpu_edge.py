@@ -66,21 +66,30 @@ def test_ragged_solve(B, O, method):
     assert abs(it - ref["iters"]) <= 2 and np.abs(x - 1).max() < 1e-7
 
 
-def test_row_longer_than_a_stage_falls_back_to_rowsplit(B, O):
-    """One dense row of 12 000 entries cannot be staged in shared memory: the plan must pick the row-split kernel
-    (and the persistent kernel must stand aside), results unchanged."""
-    n = 12000
+@pytest.mark.parametrize("n,long_rows", [(12000, [7]), (40000, [0, 20011, 39999])])
+def test_rows_longer_than_a_stage(B, O, n, long_rows, request):
+    """Dense rows of 12 000 / 40 000 entries cannot be staged in shared memory in one piece.  Kernel-per-phase path: the
+    plan picks the row-split kernel.  Persistent kernel: the planner cuts such a row into chunk tiles that the whole CTA
+    multiplies cooperatively (plan.cpp / mega.cu), so the device-resident loop stays in use.  Results unchanged."""
     A = sp.lil_matrix(_ragged(n, 5, 6))
-    A[7, :] = -1e-3
-    A[7, 7] = 20.0
+    for r in long_rows:
+        A[r, :] = -1e-3
+        A[r, r] = 0.002 * n + 10.0
     blk, n, ptr, col, val = _block(B, A)
     x = np.random.default_rng(4).standard_normal(n)
     assert rel_err(B.spmv_ovlap(blk, x), O.spmv(n, ptr, col, val, x, long_double=True)) <= 1e-13
     b = B.spmv_ovlap(blk, np.ones(n))
     xs = np.zeros(n)
     it = B.bicgstab(blk, xs, b)
-    assert B.last_stats()["spmv_kind"] == 1                  # rowsplit
+    st = B.last_stats()
+    assert st["spmv_kind"] == 1                               # stand-alone SpMV plan: rowsplit
+    if "mega" in request.node.name:
+        assert st["kernel_launches"] <= 8                     # ... and the loop still ran as ONE persistent kernel
     ref = O.solve("bicgstab", n, ptr, col, val, O.spmv(n, ptr, col, val, np.ones(n)), tol=1e-10, max_iter=500)
+    m = min(10, it, ref["iters"])
+    hist = B.last_history()
+    got, want = np.sqrt(hist[1:m + 1]), np.sqrt(ref["hist"][1:m + 1])
+    assert np.all(np.abs(got - want) <= 1e-10 * want + 1e-15)
     assert abs(it - ref["iters"]) <= 2 and np.abs(xs - 1).max() < 1e-7
 
 
