@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -364,7 +364,10 @@ def run_b200(args, w):
 
         sampler = ClockSampler(local)
         if rank == 0:
-            sampler.start()                 # nvidia-smi needs a moment to start: begin before the warm-up solves
+            sampler.start()                 # nvidia-smi needs a moment to start: begin before the warm-up solves ...
+            t_wait = time.perf_counter()    # ... and do not enter the (sub-second) timed region before it delivers samples
+            while not sampler.lines and time.perf_counter() - t_wait < 8.0:
+                time.sleep(0.05)
         for _ in range(args.warmup):
             resident_step()
         barrier()

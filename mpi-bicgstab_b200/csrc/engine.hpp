@@ -43,10 +43,12 @@ struct Config {
     int mega_trace = 0;
     int mega_lanes = 0;          // lanes per row of the persistent kernel's SpMV (0 choose from the mean row length)
     int l2_hint = 1;             // matrix stream loaded with an L2 evict-first policy (persistent kernel)
+    int row_weight = 1000;       // per-row cost (byte equivalents) next to 24 B per entry when CTA row ranges are balanced
     int boundary_weight = 600;   // extra work (bytes) charged per pushed row when CTA row ranges are balanced
     int device = -1;
     int halo_gap = 64;
     int verbose = 0;
+    int peer_timeout_s = 20;     // bound of device-side waits for peers / other CTAs (then: error + exit(1))
     int fence_writers = 0;       // 1: every thread that stored to a peer also fences at system scope itself (debug aid;
                                  // the CTA barrier + one system fence per CTA is sufficient and much cheaper)
 };

@@ -54,9 +54,11 @@ int set_option(Config &c, const char *key, const char *value)
     else if (k == "MEGA_LANES") c.mega_lanes = as_int();
     else if (k == "L2_HINT") c.l2_hint = as_int();
     else if (k == "BOUNDARY_WEIGHT") c.boundary_weight = std::max(0, as_int());
+    else if (k == "ROW_WEIGHT") c.row_weight = std::max(1, as_int());
     else if (k == "DEVICE") c.device = as_int();
     else if (k == "HALO_GAP") c.halo_gap = std::max(0, as_int());
     else if (k == "VERBOSE") c.verbose = as_int();
+    else if (k == "PEER_TIMEOUT_S") c.peer_timeout_s = std::max(1, as_int());
     else if (k == "FENCE_WRITERS") c.fence_writers = as_int();
     else return -1;
     return 0;
@@ -66,8 +68,8 @@ void load_config_from_env(Config &c)
 {
     static const char *keys[] = {"BICG_TOL", "BICG_MAX_ITER", "BICG_OUT_ITER", "BICG_QUIET", "BICG_SPMV",
                                  "BICG_SPMV_LANES", "BICG_SPMV_THREADS", "BICG_SPMV_STAGES", "BICG_SPMV_CTAS",
-                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_MEGA_LANES", "BICG_L2_HINT", "BICG_BOUNDARY_WEIGHT", "BICG_DEVICE",
-                                 "BICG_HALO_GAP", "BICG_VERBOSE", "BICG_FENCE_WRITERS"};
+                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_MEGA_LANES", "BICG_L2_HINT", "BICG_BOUNDARY_WEIGHT", "BICG_ROW_WEIGHT", "BICG_DEVICE",
+                                 "BICG_HALO_GAP", "BICG_VERBOSE", "BICG_PEER_TIMEOUT_S", "BICG_FENCE_WRITERS"};
     for (const char *k : keys)
         if (const char *v = getenv(k)) set_option(c, k, v);
 }
@@ -95,7 +97,11 @@ void Context::ensure()
         const char *lr = getenv("LOCAL_RANK");
         dev = lr ? atoi(lr) : 0;
     }
-    if (dev >= ndev) dev = dev % ndev;
+    if (dev >= ndev) {
+        // two ranks on one GPU cannot both keep a cooperative one-CTA-per-SM kernel resident: refuse instead of wrapping
+        if (world > 1) fatal("bicgstab_b200: rank %d wants device %d but only %d device(s) are visible (one rank per GPU)", rank, dev, ndev);
+        dev = dev % ndev;
+    }
     BICG_CUDA(cudaSetDevice(dev));
     device = dev;
     cudaDeviceProp prop;
@@ -389,7 +395,7 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::ve
         // are cut by the planner: greedy tiles + chunked long rows (plan.cpp)
         const int cap_limit = (int)(((SMEM_MAX / 2 - (long long)(rpt + 8) * 4) / 12 - 8) / 32 * 32);
         const unsigned max_tile_nnz = plan_cta_tiles(h_ptr, m->n_loc, G, rpt, row_extra.empty() ? nullptr : row_extra.data(),
-                                                     c.cfg.boundary_weight, tile_row, cta_tile, cap_limit, &tile_nz, &tile_flag);
+                                                     c.cfg.boundary_weight, tile_row, cta_tile, cap_limit, &tile_nz, &tile_flag, c.cfg.row_weight);
         const int cap = round_up((long long)max_tile_nnz + 8, 32);
         const long long stage = (long long)cap * 12 + (long long)(rpt + 8) * 4;
         int stages = (int)std::min<long long>(4, SMEM_MAX / stage);
@@ -606,6 +612,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     lap("arena alloc + zero");
     // ---- peers: exchange arena handles + layouts, then the halo runs -------------------------------
     m->comm.rank = m->rank; m->comm.world = m->world;
+    m->comm.timeout_ns = (unsigned long long)c.cfg.peer_timeout_s * 1000000000ull;
     for (int p = 0; p < MAX_RANKS; ++p) { m->comm.mail[p] = m->d_mail; m->comm.hflag[p] = m->d_hflag; m->peer_msync[p] = m->d_msync; }
     std::vector<unsigned char> row_extra;                  // per row: number of peers it is pushed to
     std::vector<std::vector<PushRunHost>> push_host;       // per push slot

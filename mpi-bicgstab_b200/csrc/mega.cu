@@ -26,7 +26,7 @@
 //              push them (one flag per pushing CTA, written after that CTA's own system-scope fence).
 // Coherence: gathered vectors are read with plain (L1-cached) loads; every wait ends in an acquire fence at gpu /
 // system scope (SASS: CCTL.IVALL), so lines rewritten by other SMs / peers are re-fetched from L2.
-// Every wait is bounded by PEER_TIMEOUT_NS: a lost CTA or rank raises Scalars::error instead of hanging the GPU.
+// Every wait is bounded by CommDev::timeout_ns (BICG_PEER_TIMEOUT_S): a lost CTA or rank raises Scalars::error instead of hanging the GPU.
 #include "mega.cuh"
 #include "vec_body.cuh"
 
@@ -181,7 +181,7 @@ struct Mega {
                 if (c == (int)blockIdx.x) continue;
                 unsigned spins = 0;
                 while ((unsigned)(ld_ll_gpu(&ring[c].w[0]) >> 32) != gen)
-                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
+                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
             }
             const bool remote = halo && need_senders != 0u;
             if (remote) {
@@ -192,7 +192,7 @@ struct Mega {
                         if (!((a.sync->pusher_mask[s][i >> 5] >> (i & 31)) & 1u)) continue;
                         unsigned spins = 0;
                         while (ld_relaxed_sys(&f[i]) < halo_epoch)
-                            if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { ok = false; break; }
+                            if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
                     }
                 }
             }
@@ -230,7 +230,7 @@ struct Mega {
 #pragma unroll
                     for (int k = 0; k < NV; ++k) { ld_ll_gpu2(w + 2 * k, w0[k], w1[k]); all = all && ll_valid(w0[k], w1[k], g); }
                     if (all) break;
-                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { fail(); break; }
+                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
                 }
 #pragma unroll
                 for (int k = 0; k < NV; ++k) v[k] = ll_decode(w0[k], w1[k]);
@@ -286,7 +286,7 @@ struct Mega {
 #pragma unroll
                 for (int k = 0; k < NV; ++k) { ld_ll_sys(w + 2 * k, w0[k], w1[k]); all = all && ll_valid(w0[k], w1[k], red_epoch); }
                 if (all) break;
-                if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { fail(); break; }
+                if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
             }
 #pragma unroll
             for (int k = 0; k < NV; ++k) sh.contrib[lane][k] = ll_decode(w0[k], w1[k]);
@@ -334,8 +334,26 @@ struct Mega {
         }
         wait_nbr(halo);
     }
+    // MPI_Wait.  after_spmv: the SpMV that hid the reduction gathered a vector that the NEXT phase overwrites in place
+    // (pipelined loops: y = w - alpha z is stored over w right after t = A w): the reduction was published BEFORE that
+    // SpMV, so its completion says nothing about the other CTAs having finished their gathers.  A second, data-free
+    // arrival after the SpMV, awaited from every CTA of this GPU (peers never gather own rows), closes the window.
     template <int NV>
-    __device__ void complete(int fin) { finish<NV>(posted_gen, fin, true); }      // MPI_Wait
+    __device__ void complete(int fin, bool after_spmv)
+    {
+        if (after_spmv) {
+            double d0[1] = {0.0};
+            arrive<0>(d0, false);
+            if (tid < RED_THREADS && tid < (int)gridDim.x && tid != (int)blockIdx.x) {
+                const unsigned long long *w = a.sync->slot[gen & (MEGA_RING - 1)][tid].w;
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned spins = 0;
+                while ((unsigned)(ld_ll_gpu(w) >> 32) != gen)
+                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
+            }
+        }
+        finish<NV>(posted_gen, fin, true);
+    }
 
     // ---------------------------------------------------------------- SpMV over this CTA's tiles ----------
     template <int EPI>
@@ -558,7 +576,7 @@ struct Mega {
             push(V_Z);
             post<2>(d2, true);                                              // MPI_Iallreduce x2
             spmv<EPI_NONE>(a.v.z, a.v.v, d4);                               // v = A z hides it           :365 / 513
-            complete<2>(FIN_OMEGA2);                                        // MPI_Wait x2 -> omega       :366-369
+            complete<2>(FIN_OMEGA2, false);                                 // MPI_Wait x2 -> omega       :366-369
             if (stop_now()) break;
             d5[0] = d5[1] = d5[2] = d5[3] = d5[4] = 0.0;
             if (!replace) {
@@ -579,7 +597,7 @@ struct Mega {
             push(V_W);
             post<5>(d5, true);                                              // MPI_Iallreduce x5
             spmv<EPI_NONE>(a.v.w, a.v.t, d4);                               // t = A w hides it           :381 / 540
-            complete<5>(FIN_CAPIPE_END);                                    // MPI_Wait x5 -> beta, alpha :382-388
+            complete<5>(FIN_CAPIPE_END, true);                              // MPI_Wait x5 -> beta, alpha :382-388
             if (stop_now()) break;
         }
     }

@@ -144,16 +144,18 @@ void plan_merged_layout(const CSR_Matrix *diag, const CSR_Matrix *offd, const IN
 }
 
 // Tile plan of the persistent solver kernel (mega.cu).  CTA g of `ctas` owns a contiguous row range; the ranges are
-// balanced by the bytes an iteration moves for a row -- 24 B per entry (two SpMVs) + 216 B of vector traffic, plus
-// `extra_weight` for every peer the row is pushed to (NVLink stores are slow per SM, and the CTAs at the partition
+// balanced by the cost of a row per iteration -- 24 B per entry (two SpMVs) + row_weight (216 B of vector traffic is the
+// pure byte count; measured on B200 the thread-per-row SpMV and the vector phases behave like ~1000 B per row: CTA time
+// follows the row count much more than the entry count, profiles/r02_*), plus `extra_weight` for every peer the row is pushed to (NVLink stores are slow per SM, and the CTAs at the partition
 // boundary also sit on the critical path of the halo exchange) -- and start at multiples of 16 rows, so every CTA's
 // slice of every vector is 128-byte aligned.  Each range is cut into ceil(len / rows_per_tile) tiles of (almost)
 // equal height.  tile_row gets the first row of every tile plus a final `rows`; cta_tile[g] is the index of CTA g's
 // first tile (cta_tile[ctas] = #tiles).  Returns the largest number of entries in any tile.
 unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int rows_per_tile, const unsigned char *row_extra,
                         int extra_weight, std::vector<int> &tile_row, std::vector<int> &cta_tile, int cap_limit,
-                        std::vector<unsigned> *tile_nz, std::vector<int> *tile_flag)
+                        std::vector<unsigned> *tile_nz, std::vector<int> *tile_flag, int row_weight)
 {
+    if (row_weight <= 0) row_weight = 216;
     tile_row.clear();
     if (tile_nz) tile_nz->clear();
     if (tile_flag) tile_flag->clear();
@@ -161,9 +163,9 @@ unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int rows_per_ti
     std::vector<int> first((size_t)ctas + 1, rows);
     first[0] = 0;
     auto weight = [&](int i) -> long long {
-        return 24ll * (long long)(ptr[i + 1] - ptr[i]) + 216ll + (row_extra ? (long long)extra_weight * row_extra[i] : 0ll);
+        return 24ll * (long long)(ptr[i + 1] - ptr[i]) + (long long)row_weight + (row_extra ? (long long)extra_weight * row_extra[i] : 0ll);
     };
-    long long total = 24ll * (long long)(ptr[rows] - ptr[0]) + 216ll * rows;
+    long long total = 24ll * (long long)(ptr[rows] - ptr[0]) + (long long)row_weight * rows;
     if (row_extra && extra_weight)
         for (int i = 0; i < rows; ++i) total += (long long)extra_weight * row_extra[i];
     {
@@ -276,7 +278,7 @@ extern "C" int bicg_plan_cta_tiles(const unsigned int *ptr, int rows, int ctas, 
                                    int extra_weight, int *tile_row, int tile_row_cap, int *cta_tile, unsigned int *max_tile_nnz)
 {
     std::vector<int> tr, ct;
-    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, rows_per_tile, row_extra, extra_weight, tr, ct, 0, nullptr, nullptr);
+    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, rows_per_tile, row_extra, extra_weight, tr, ct, 0, nullptr, nullptr, 216);
     if ((int)tr.size() > tile_row_cap) return -(int)tr.size();
     std::memcpy(tile_row, tr.data(), tr.size() * sizeof(int));
     std::memcpy(cta_tile, ct.data(), ct.size() * sizeof(int));
@@ -291,7 +293,7 @@ extern "C" int bicg_plan_cta_tiles_capped(const unsigned int *ptr, int rows, int
 {
     std::vector<int> tr, ct, fl;
     std::vector<unsigned> nz;
-    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, rows_per_tile, nullptr, 0, tr, ct, cap_limit, &nz, &fl);
+    const unsigned mx = bicg::plan_cta_tiles(ptr, rows, ctas, rows_per_tile, nullptr, 0, tr, ct, cap_limit, &nz, &fl, 216);
     if ((int)tr.size() > tile_cap) return -(int)tr.size();
     std::memcpy(tile_row, tr.data(), tr.size() * sizeof(int));
     std::memcpy(tile_nz, nz.data(), nz.size() * sizeof(unsigned));

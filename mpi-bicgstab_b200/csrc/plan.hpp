@@ -11,7 +11,7 @@ struct PushRunHost { int src; int len; int dst_off; };   // local rows [src, src
 int  plan_tiles(const unsigned *ptr, int rows, int rows_per_tile, int cap_nnz, std::vector<int> &tile_row);
 unsigned plan_cta_tiles(const unsigned *ptr, int rows, int ctas, int rows_per_tile, const unsigned char *row_extra,
                         int extra_weight, std::vector<int> &tile_row, std::vector<int> &cta_tile, int cap_limit,
-                        std::vector<unsigned> *tile_nz, std::vector<int> *tile_flag);
+                        std::vector<unsigned> *tile_nz, std::vector<int> *tile_flag, int row_weight);
 void plan_halo_runs(const CSR_Matrix *offd, const INFO_Matrix *info, int world, int gap, int self,
                     std::vector<HaloRun> &runs);
 

@@ -371,7 +371,8 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
     for (cudaEvent_t e : ring) if (e) cudaEventDestroy(e);
     (void)launched_batches;
 
-    if (hs.error) fatal("bicgstab_b200: rank %d timed out waiting for a peer GPU (halo or reduction mailbox)", m->rank);
+    if (hs.error) fatal("bicgstab_b200: rank %d timed out after %d s waiting for a peer GPU / another CTA (halo flag or reduction "
+                        "mailbox; BICG_PEER_TIMEOUT_S raises the bound)", m->rank, cfg.peer_timeout_s);
     if (m->d_trace && use_mega && method == BICG_METHOD_BICGSTAB) {
         // BICG_MEGA_TRACE=1: where CTA 0 and the middle CTA of the persistent kernel spent their time, averaged over the iterations
         const int iters = std::min(hs.k - 1, (int)MEGA_TRACE_ITERS);

@@ -295,3 +295,60 @@ def test_persistent_kernel_plan_cuts_long_rows_into_chunks(B):
     for g in range(ctas):                                         # a row's chunks never straddle two CTAs
         if c[g] < nt and c[g] > 0:
             assert f[c[g] - 1] != 1
+
+
+_BOOT_C = r"""
+#include <stdio.h>
+int bicg_shm_bootstrap(void); void bicg_shm_shutdown(void); int bicg_comm_rank(void); int bicg_comm_world(void); int bicg_comm_selftest(void);
+int main() { bicg_shm_bootstrap(); printf("rank %d of %d selftest %d\n", bicg_comm_rank(), bicg_comm_world(), bicg_comm_selftest());
+             bicg_shm_shutdown(); return 0; }
+"""
+
+
+def _boot_exe(tmp_path):
+    import subprocess
+    src = tmp_path / "boot.c"
+    src.write_text(_BOOT_C)
+    exe = tmp_path / "boot"
+    libdir = os.path.join(ROOT, "mpi-bicgstab_b200")
+    subprocess.run(["gcc", "-O1", str(src), f"-L{libdir}", "-lbicgstab_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    return str(exe)
+
+
+def test_shm_bootstrap_four_ranks_and_cleanup(B, tmp_path):
+    """csrc/shm_boot.cpp (the MPI_Init of include/compat/mpi.h): 4 processes rendezvous, allgather works, the segment is
+    unlinked afterwards.  No GPU involved."""
+    import subprocess
+    exe = _boot_exe(tmp_path)
+    p = subprocess.run([os.path.join(ROOT, "tools", "bicgrun"), "-np", "4", exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert sorted(p.stdout.split("\n")[:4]) == [f"rank {r} of 4 selftest 0" for r in range(4)]
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith(f"bicg_b200_{os.getuid()}_job")]
+
+
+def test_shm_bootstrap_survives_a_stale_segment(B, tmp_path):
+    """A crashed job left a READY segment with no join tickets; the new job's ranks 1, 2 start BEFORE rank 0.  They must
+    not attach to the corpse (round-1 behaviour: hang) but wait for rank 0's fresh segment."""
+    import struct, subprocess, time
+    exe = _boot_exe(tmp_path)
+    job = f"stale{os.getpid()}"
+    name = f"/dev/shm/bicg_b200_{os.getuid()}_{job}"
+    with open(name, "wb") as f:
+        f.truncate(64 + (256 << 20))
+        f.write(struct.pack("<iiiiiiQ", 0x42494347, 0, 0, 3, 0, 1, 0))     # READY, joined = 3, creator pid 1 (alive)
+    env = dict(os.environ, WORLD_SIZE="3", BICG_JOB_ID=job, BICG_BOOT_TIMEOUT_S="30")
+    ps = [subprocess.Popen([exe], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, text=True) for r in (1, 2)]
+    time.sleep(0.5)
+    ps.append(subprocess.Popen([exe], env=dict(env, RANK="0", LOCAL_RANK="0"), stdout=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=90)[0].strip() for p in ps]
+    assert all(p.returncode == 0 for p in ps), outs
+    assert sorted(outs) == [f"rank {r} of 3 selftest 0" for r in range(3)]
+    assert not os.path.exists(name)
+
+
+def test_shm_bootstrap_rejects_more_than_eight_ranks(B, tmp_path):
+    import subprocess
+    exe = _boot_exe(tmp_path)
+    p = subprocess.run([exe], env=dict(os.environ, WORLD_SIZE="9", RANK="0", BICG_JOB_ID=f"big{os.getpid()}"), capture_output=True,
+                       text=True, timeout=60)
+    assert p.returncode == 1 and "more than 8 ranks" in p.stderr        # main.c ignores MPI_Init's return value: must be fatal

@@ -226,7 +226,7 @@ _REF_ITERS = {}
 def test_bench_matrix_parity(B, O):
     """The BASELINE config-2 matrix itself (T' surrogate with the bench's p0 = 14: 1,601,613 rows, 23,616,325 entries),
     tol 1e-8: H-level against the oracle, C-level against the reference's own sources compiled in place
-    (oracle/_ref/ref_driver_strict, P = 1; about 45 s of CPU, run once per session)."""
+    (oracle/_ref/ref_driver_fast, P = 1; about 45 s of CPU, run once per session)."""
     f, n, ptr, col, val = big_csr("stencil15", 117, 14.0)
     blk = B.gen_block("stencil15", 117, 14.0)
     assert blk.n == n and blk.nnz_loc == val.size
@@ -243,9 +243,13 @@ def test_bench_matrix_parity(B, O):
     ref10 = O.solve("bicgstab", n, ptr, col, val, b_ref, tol=1e-8, max_iter=10)
     got, want = np.sqrt(hist[1:11]), np.sqrt(ref10["hist"][1:11])
     assert np.all(np.abs(got - want) <= 1e-10 * want + H_FLOOR), np.abs(got - want) / want
-    if O.have_ref("ref_driver_strict"):
+    # C-level partner: the reference as a user builds it (gcc -O3: FMA contraction on, like the GPU's fma chain).  At this
+    # size and tolerance the reference's own builds disagree by more than the 2 % rule -- the strict IEEE build
+    # (-O2 -ffp-contract=off) needs 380 iterations where the -O3 build needs 333 (measured on the same box, round 2) -- so the
+    # iteration count is compared with the -O3 build and must in any case lie inside the spread of the reference's builds.
+    if O.have_ref("ref_driver_fast"):
         if "bicgstab" not in _REF_ITERS:
-            _REF_ITERS["bicgstab"] = O.ref_driver("bicgstab", f, P=1, rhs="a1", tol=1e-8, max_iter=1000, flavour="strict",
+            _REF_ITERS["bicgstab"] = O.ref_driver("bicgstab", f, P=1, rhs="a1", tol=1e-8, max_iter=1000, flavour="fast",
                                                   want_vectors=False, timeout=1200)["iters"]
         ref_it = _REF_ITERS["bicgstab"]
         assert abs(it - ref_it) <= max(2, int(0.02 * ref_it)), (it, ref_it)
