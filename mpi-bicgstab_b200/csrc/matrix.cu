@@ -385,6 +385,11 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::ve
     const int G = std::min(c.sm_count, MEGA_MAX_CTAS);
     const long long SMEM_MAX = 222 * 1024;
     const int lanes = c.cfg.mega_lanes > 0 ? c.cfg.mega_lanes : mega_lanes_for(m->mean_row);
+    // BICG_MEGA=1 (default): the persistent kernel where it wins -- thread-per-row plans (banded matrices, short rows).  On
+    // long-row matrices (cfg 5: 32 random entries per row) the loop is bound by L2 sector throughput of the gathers, not by
+    // launch / barrier latency, and the autotuned kernel-per-phase SpMV is faster (profiles/r02a_n1_random_block.log);
+    // BICG_MEGA=2 or an explicit BICG_MEGA_LANES forces the persistent kernel there too.
+    if (lanes != 1 && c.cfg.mega != 2 && c.cfg.mega_lanes == 0) return;
     for (int threads : {512, 256}) {
         if (c.cfg.mega_threads && c.cfg.mega_threads != threads) continue;
         if (!mega_has_variant(threads, lanes)) continue;

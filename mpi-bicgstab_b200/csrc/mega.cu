@@ -309,7 +309,9 @@ struct Mega {
             if (tid < 32) mail_reduce<NV>();
         }
         if (tid == 0) {
-            fence_gpu();
+            // no acquire fence here: a reduction is never directly followed by a gather of other CTAs' rows (a neighbour
+            // wait with its own fence always sits in between), and the writes that follow are control-dependent on the
+            // polls above
             if (sh.flags[3]) { sh.sc.error = 1; sh.sc.done = 1; }
             else finalize(fin, &sh.sc, blockIdx.x == 0 ? a.hist : nullptr, sh.tot);
         }

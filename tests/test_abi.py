@@ -352,3 +352,49 @@ def test_shm_bootstrap_rejects_more_than_eight_ranks(B, tmp_path):
     p = subprocess.run([exe], env=dict(os.environ, WORLD_SIZE="9", RANK="0", BICG_JOB_ID=f"big{os.getpid()}"), capture_output=True,
                        text=True, timeout=60)
     assert p.returncode == 1 and "more than 8 ranks" in p.stderr        # main.c ignores MPI_Init's return value: must be fatal
+
+
+_MPI_BOOT_C = r"""
+/* The maintainer-side line of INTEGRATION.md section 1: an MPI program registers MPI itself as the library's bootstrap
+ * transport.  Compiled here against the oracle's functional mini-MPI (fork + shm, oracle/mini_mpi.c) because the image has
+ * no MPI installation; with a real MPI the callback body is MPI_Allgather(s, n, MPI_BYTE, r, n, MPI_BYTE, MPI_COMM_WORLD). */
+#include <stdio.h>
+#include <mpi.h>
+#include "bicgstab_b200.h"
+static int ag(void *c, const void *s, void *r, size_t n)
+{
+    int np, cnt[8], dsp[8]; MPI_Request q; (void)c;
+    MPI_Comm_size(MPI_COMM_WORLD, &np);
+    for (int p = 0; p < np; ++p) { cnt[p] = (int)n; dsp[p] = (int)(p * n); }
+    MPI_Iallgatherv(s, (int)n, MPI_CHAR, r, cnt, dsp, MPI_CHAR, MPI_COMM_WORLD, &q);
+    return MPI_Wait(&q, MPI_STATUS_IGNORE);
+}
+int main(int argc, char **argv)
+{
+    int np, me;
+    MPI_Init(&argc, &argv);
+    MPI_Comm_size(MPI_COMM_WORLD, &np); MPI_Comm_rank(MPI_COMM_WORLD, &me);
+    int rc = bicg_comm_init(me, np, ag, NULL);
+    printf("rank %d of %d init %d selftest %d\n", bicg_comm_rank(), bicg_comm_world(), rc, bicg_comm_selftest());
+    fflush(stdout);
+    bicg_comm_finalize();
+    MPI_Finalize();
+    return 0;
+}
+"""
+
+
+def test_mpi_program_registers_mpi_as_bootstrap_transport(B, tmp_path):
+    """INTEGRATION.md section 1, exercised: bicg_comm_init with an MPI-allgather callback inside an MPI program (the oracle's
+    mini-MPI stands in for the absent MPI installation), 4 ranks, the library's self-test round-trips through it.  CPU only."""
+    import subprocess
+    src = tmp_path / "mpiboot.c"
+    src.write_text(_MPI_BOOT_C)
+    exe = tmp_path / "mpiboot"
+    libdir = os.path.join(ROOT, "mpi-bicgstab_b200")
+    subprocess.run(["gcc", "-O1", f"-I{os.path.join(ROOT, 'oracle', 'mpi_stub')}", f"-I{os.path.join(ROOT, 'include')}", str(src),
+                    os.path.join(ROOT, "oracle", "mini_mpi.c"), f"-L{libdir}", "-lbicgstab_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
+                   check=True)
+    p = subprocess.run([str(exe)], env=dict(os.environ, MINI_MPI_NP="4"), capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert sorted(l for l in p.stdout.splitlines() if l.startswith("rank")) == [f"rank {r} of 4 init 0 selftest 0" for r in range(4)]

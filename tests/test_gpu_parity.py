@@ -258,12 +258,14 @@ def test_bench_matrix_parity(B, O):
     dm.destroy()
 
 
-def test_random_block_parity(B, O):
+def test_random_block_parity(B, O, request):
     """A >= 1 M-row block of the config-5 family (random, 32 entries per row, CA-BiCGStab): the long-row path of the
-    persistent kernel (LANES > 1) at size."""
+    persistent kernel (LANES > 1, forced with BICG_MEGA=2) and the autotuned kernel-per-phase path at size."""
     f, n, ptr, col, val = big_csr("random", 1_000_003, 32)
     blk = B.gen_block("random", 1_000_003, 32)
     b_ref = O.spmv(n, ptr, col, val, np.ones(n))
+    if "mega" in request.node.name:
+        B.set_options(mega=2)
     dm = B.DeviceMatrix(blk)
     B.set_options(tol=1e-10, max_iter=200)
     x = np.zeros(n)
@@ -276,4 +278,6 @@ def test_random_block_parity(B, O):
     got, want = np.sqrt(hist[1:m + 1]), np.sqrt(ref["hist"][1:m + 1])
     assert np.all(np.abs(got - want) <= 1e-10 * want + H_FLOOR), np.abs(got - want) / want
     assert abs(it - ref["iters"]) <= 2 and np.abs(x - 1.0).max() <= 1e-8
+    if "mega" in request.node.name:
+        assert st["kernel_launches"] <= 8          # the loop ran as one persistent kernel
     dm.destroy()
