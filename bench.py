@@ -231,28 +231,57 @@ def reference_sample(rr, n_iters):
     return res
 
 
+def _first_exceed(a, b, tol=1e-10):
+    """first index k (1-based iteration) where |a_k - b_k| / b_k > tol; len + 1 if never"""
+    m = min(len(a), len(b))
+    bad = np.nonzero(np.abs(a[:m] - b[:m]) > tol * np.abs(b[:m]))[0]
+    return int(bad[0]) + 1 if bad.size else m + 1
+
+
 def parity_object(rr, w, world, hist, iters):
-    """Driver-visible parity at the benchmark's own size and rank count: H-level (first 10 entries of the residual
-    history vs the oracle's P = world emulation, SURVEY.md 8(c): <= 1e-10 relative) and C-level (iterations to tol vs
-    the reference's own sources run with P = world ranks: within max(2, 2 %))."""
+    """Driver-visible parity at the benchmark's own size and rank count.
+    H-level: first 10 entries of the residual history vs the oracle's P = world emulation (SURVEY.md 8(c): <= 1e-10 relative);
+             plus the WINDOW over which the GPU history agrees with the oracle to 1e-10, next to the window over which the
+             reference's own two builds (strict IEEE vs -O3 with FMA contraction) agree with each other -- BiCGStab histories are
+             chaotic in the summation order, so agreement beyond the reference's own self-consistency window is not defined.
+    C-level: iterations to tol vs the reference's own sources (the -O3 build a user makes) run with P = world ranks: within
+             max(2, 2 %).  When that fails, the strict build of the same reference is run as well: at this size the
+             reference's builds differ from each other by more than the rule (round 2: 333 vs 380 at P = 1)."""
     O = rr.O
     n, ptr, col, val = rr.load_csr()
     method = w["method"]
     t0 = time.perf_counter()
     b = O.spmv(n, ptr, col, val, np.ones(n), P=world)
-    m = min(10, iters)
-    ref10 = O.solve(method, n, ptr, col, val, b, P=world, tol=w["tol"], max_iter=m)
-    m = min(m, ref10["iters"])
-    got, want = np.sqrt(np.asarray(hist[1:m + 1])), np.sqrt(ref10["hist"][1:m + 1])
-    rel = float(np.max(np.abs(got - want) / want)) if m else 0.0
+    W = min(40, iters)
+    ref = O.solve(method, n, ptr, col, val, b, P=world, tol=w["tol"], max_iter=W)
+    W = min(W, ref["iters"])
+    got, want = np.sqrt(np.asarray(hist[1:W + 1])), np.sqrt(ref["hist"][1:W + 1])
+    m = min(10, W)
+    rel = float(np.max(np.abs(got[:m] - want[:m]) / want[:m])) if m else 0.0
     out = {"h_level_max_rel": rel, "h_level_iters": int(m), "h_level_tol": 1e-10, "h_level_ok": bool(rel <= 1e-10),
            "h_level_oracle": f"oracle/liboracle.so, P={world} rank emulation (pinned bitwise to the compiled reference)",
+           "h_window_gpu_vs_oracle": _first_exceed(got, want) - 1,
            "iters": int(iters), "ref_iters": None, "ref_P": world, "c_level_rule": "max(2, 2 %)"}
+    try:
+        user = rr.O.ref_driver(method, rr.file, P=world, rhs="a1", tol=0.0, max_iter=W, flavour=rr.flavour, want_vectors=True,
+                               pin=True, timeout=900)
+        out["h_window_reference_builds"] = _first_exceed(np.asarray(user["res"][:W]), want) - 1
+        out["h_window_note"] = ("iterations over which the history agrees to 1e-10: GPU vs oracle, and the reference's own -O3 build "
+                                f"vs its strict build (= the oracle), first {W} iterations examined")
+    except Exception as exc:
+        out["h_window_reference_builds"] = None
+        out["h_window_note"] = f"reference history run failed: {exc!r}"
     try:
         full = rr.solve_to_tol(world, w["tol"], w["max_iter"])
         out["ref_iters"] = int(full["iters"])
         out["c_level_ok"] = bool(abs(iters - full["iters"]) <= max(2, int(0.02 * full["iters"])))
         out["ref_source"] = f"oracle/_ref/ref_driver_{rr.flavour} (the reference's own solver.c/matrix.c/vector.c), {world} ranks"
+        if not out["c_level_ok"]:
+            strict = rr.O.ref_driver(method, rr.file, P=world, rhs="a1", tol=w["tol"], max_iter=w["max_iter"], flavour="strict",
+                                     want_vectors=False, pin=True, timeout=1800)
+            lo, hi = sorted((int(full["iters"]), int(strict["iters"])))
+            out["ref_iters_strict_build"] = int(strict["iters"])
+            out["c_level_in_reference_spread"] = bool(lo - max(2, int(0.02 * lo)) <= iters <= hi + max(2, int(0.02 * hi)))
     except Exception as exc:
         out["ref_source"] = f"reference run failed: {exc!r}"
     out["seconds"] = round(time.perf_counter() - t0, 1)

@@ -59,6 +59,13 @@ __device__ __forceinline__ void tma_load_1d_hint(unsigned dst_smem, const void *
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
+// Polling etiquette: the first probes go out back to back (the last arriver normally finds everything in place), after
+// that the thread sleeps 64 .. 256 ns between probes -- 148 CTAs spinning flat out on the same 148 cache lines delay the
+// very stores they are waiting for.
+__device__ __forceinline__ void poll_pause(unsigned spins)
+{
+    if (spins > 2u) __nanosleep(spins > 16u ? 256u : (spins > 6u ? 128u : 64u));
+}
 template <int LANES>
 __device__ __forceinline__ double lanes_sum(double v)
 {
@@ -180,8 +187,10 @@ struct Mega {
             for (int c = dep_lo + lane; c <= dep_hi; c += 32) {
                 if (c == (int)blockIdx.x) continue;
                 unsigned spins = 0;
-                while ((unsigned)(ld_ll_gpu(&ring[c].w[0]) >> 32) != gen)
-                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
+                while ((unsigned)(ld_ll_gpu(&ring[c].w[0]) >> 32) != gen) {
+                    poll_pause(++spins);
+                    if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
+                }
             }
             const bool remote = halo && need_senders != 0u;
             if (remote) {
@@ -191,8 +200,10 @@ struct Mega {
                     for (int i = lane; i < MEGA_MAX_CTAS; i += 32) {
                         if (!((a.sync->pusher_mask[s][i >> 5] >> (i & 31)) & 1u)) continue;
                         unsigned spins = 0;
-                        while (ld_relaxed_sys(&f[i]) < halo_epoch)
-                            if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
+                        while (ld_relaxed_sys(&f[i]) < halo_epoch) {
+                            poll_pause(++spins);
+                            if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
+                        }
                     }
                 }
             }
@@ -230,7 +241,8 @@ struct Mega {
 #pragma unroll
                     for (int k = 0; k < NV; ++k) { ld_ll_gpu2(w + 2 * k, w0[k], w1[k]); all = all && ll_valid(w0[k], w1[k], g); }
                     if (all) break;
-                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
+                    poll_pause(++spins);
+                    if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
                 }
 #pragma unroll
                 for (int k = 0; k < NV; ++k) v[k] = ll_decode(w0[k], w1[k]);
@@ -286,7 +298,8 @@ struct Mega {
 #pragma unroll
                 for (int k = 0; k < NV; ++k) { ld_ll_sys(w + 2 * k, w0[k], w1[k]); all = all && ll_valid(w0[k], w1[k], red_epoch); }
                 if (all) break;
-                if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
+                poll_pause(++spins);
+                if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
             }
 #pragma unroll
             for (int k = 0; k < NV; ++k) sh.contrib[lane][k] = ll_decode(w0[k], w1[k]);
@@ -301,12 +314,13 @@ struct Mega {
     }
     // complete the reduction published at generation g and evaluate the scalar recurrence `fin` in this CTA's copy
     template <int NV>
-    __device__ void finish(unsigned g, int fin, bool posted)
+    __device__ void finish(unsigned g, int fin, bool posted, bool tr = false)
     {
-        if (a.comm.world == 1) local_reduce<NV>(g);
+        if (a.comm.world == 1) { local_reduce<NV>(g); if (tr) mark(12); }
         else {
-            if (blockIdx.x == 0 && !posted) { local_reduce<NV>(g); if (tid < 32) post_mail<NV>(); }
+            if (blockIdx.x == 0 && !posted) { local_reduce<NV>(g); if (tr) mark(12); if (tid < 32) post_mail<NV>(); if (tr) mark(13); }
             if (tid < 32) mail_reduce<NV>();
+            if (tr) mark(14);
         }
         if (tid == 0) {
             // no acquire fence here: a reduction is never directly followed by a gather of other CTAs' rows (a neighbour
@@ -318,11 +332,12 @@ struct Mega {
         nbar(1, CT);
     }
     template <int NV>
-    __device__ void reduce(double (&dot)[NV], int fin)          // blocking sync point (MPI_Iallreduce + MPI_Wait)
+    __device__ void reduce(double (&dot)[NV], int fin, bool tr = false)   // blocking sync point (MPI_Iallreduce + MPI_Wait)
     {
         arrive<NV>(dot, false);
+        if (tr) mark(11);
         if (a.comm.world > 1) ++red_epoch;
-        finish<NV>(gen, fin, false);
+        finish<NV>(gen, fin, false, tr);
     }
     template <int NV>
     __device__ void post(double (&dot)[NV], bool halo)          // MPI_Iallreduce (+ the halo of the SpMV that hides it)
@@ -350,8 +365,10 @@ struct Mega {
                 const unsigned long long *w = a.sync->slot[gen & (MEGA_RING - 1)][tid].w;
                 const unsigned long long t0 = globaltimer_ns();
                 unsigned spins = 0;
-                while ((unsigned)(ld_ll_gpu(w) >> 32) != gen)
-                    if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
+                while ((unsigned)(ld_ll_gpu(w) >> 32) != gen) {
+                    poll_pause(++spins);
+                    if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
+                }
             }
         }
         finish<NV>(posted_gen, fin, true);
@@ -498,7 +515,7 @@ struct Mega {
             spmv<EPI_RH_Y>(a.v.p, a.v.s, d4);                               // s = A p, (r#,s)           :88-91
             mark(1);
             d1[0] = d4[0];
-            reduce<1>(d1, FIN_BICG_ALPHA);                                  // alpha                      :93
+            reduce<1>(d1, FIN_BICG_ALPHA, true);                            // alpha                      :93
             mark(2);
             if (stop_now()) break;
             vec<PH_BICG_Q>(d0);                                             // q = r - alpha s            :94

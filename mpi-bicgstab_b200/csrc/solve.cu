@@ -386,11 +386,24 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
             for (int it = 1; it < iters; ++it)
                 for (int k = 0; k < 10; ++k)
                     sum[k] += (double)(tr[base + (size_t)it * MEGA_TRACE_SLOTS + k + 1] - tr[base + (size_t)it * MEGA_TRACE_SLOTS + k]);
-            char line[1024]; int o = 0;
+            char line[1536]; int o = 0;
             o += snprintf(line + o, sizeof(line) - o, "[bicg mega trace r%d] us per iteration (CTA %s):", m->rank, who ? "mid" : "0");
             double tot = 0;
             for (int k = 0; k < 10; ++k) { o += snprintf(line + o, sizeof(line) - o, " %s %.2f |", names[k], sum[k] / std::max(1, iters - 1) * 1e-3); tot += sum[k]; }
-            snprintf(line + o, sizeof(line) - o, " total %.2f\n", tot / std::max(1, iters - 1) * 1e-3);
+            o += snprintf(line + o, sizeof(line) - o, " total %.2f", tot / std::max(1, iters - 1) * 1e-3);
+            // inside the alpha sync point: arrive (CTA sum + release fence + slot store) | all local slots seen | posted to the
+            // peers' mailboxes (CTA 0, N > 1) | every rank's sums seen
+            double sub[4] = {0};
+            const int mk[5] = {1, 11, 12, 13, 14};
+            for (int it = 1; it < iters; ++it) {
+                unsigned long long prev = tr[base + (size_t)it * MEGA_TRACE_SLOTS + mk[0]];
+                for (int k = 1; k < 5; ++k) {
+                    const unsigned long long t = tr[base + (size_t)it * MEGA_TRACE_SLOTS + mk[k]];
+                    if (t) { sub[k - 1] += (double)(t - prev); prev = t; }
+                }
+            }
+            snprintf(line + o, sizeof(line) - o, " || alpha sync: arrive %.2f local %.2f post %.2f mail %.2f\n", sub[0] / std::max(1, iters - 1) * 1e-3,
+                     sub[1] / std::max(1, iters - 1) * 1e-3, sub[2] / std::max(1, iters - 1) * 1e-3, sub[3] / std::max(1, iters - 1) * 1e-3);
             fputs(line, stderr);
         }
     }
