@@ -398,7 +398,7 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::ve
         std::vector<unsigned> tile_nz;
         // a stage must hold one tile; at least two stages must fit.  Tiles (or single rows) with more entries than that
         // are cut by the planner: greedy tiles + chunked long rows (plan.cpp)
-        const int cap_limit = (int)(((SMEM_MAX / 2 - (long long)(rpt + 8) * 4) / 12 - 8) / 32 * 32);
+        const int cap_limit = (int)(((SMEM_MAX / 2 - (long long)(rpt + 8) * 4) / 12) / 32 * 32) - 64;   // cap = roundup(max + 8, 32) must still fit twice
         const unsigned max_tile_nnz = plan_cta_tiles(h_ptr, m->n_loc, G, rpt, row_extra.empty() ? nullptr : row_extra.data(),
                                                      c.cfg.boundary_weight, tile_row, cta_tile, cap_limit, &tile_nz, &tile_flag, c.cfg.row_weight);
         const int cap = round_up((long long)max_tile_nnz + 8, 32);

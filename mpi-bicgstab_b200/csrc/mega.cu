@@ -127,6 +127,9 @@ struct Mega {
     int dep_lo, dep_hi;           // CTAs owning the own columns this CTA's rows reference
     unsigned need_senders;        // ranks whose halo pushes this CTA's rows reference
     unsigned push_slots;          // push slots (peers) that need rows of this CTA
+    int gs_lo, gs_hi;             // ghost slots this CTA keeps up to date itself (multi-GPU bicgstab: redundant recurrences)
+    unsigned gs_senders;          // ranks that fill those slots
+    bool reads_ghost;             // this CTA's rows gather ghost columns
     size_t stage_bytes;
     int trace_it, trace_who;
 
@@ -143,8 +146,12 @@ struct Mega {
     // ---------------------------------------------------------------- arrive ------------------------------
     // Publish NV partial sums (NV = 0: presence only) for generation ++gen.  halo: this synchronisation point also
     // carries a halo exchange -- CTAs that pushed rows to peers fence at system scope and raise their flag there.
+    // release: the arrival also PUBLISHES this CTA's stores of the phase (rows that other CTAs / peers gather after
+    // waiting for it): CTA barrier + release fence before the words go out.  A pure reduction arrival does not need it:
+    // the reduced values travel inside the words, nobody gathers this CTA's rows before its next releasing arrival (a
+    // neighbour wait always precedes a gather), and its own earlier gathers completed before the dots that depend on them.
     template <int NV>
-    __device__ void arrive(double (&dot)[NV > 0 ? NV : 1], bool halo)
+    __device__ void arrive(double (&dot)[NV > 0 ? NV : 1], bool halo, bool release = true)
     {
         // a CTA barrier (inside cblock_sum, or the explicit one) puts every consumer's stores of the phase before the fence
         if (NV > 0) cblock_sum<(NV > 0 ? NV : 1), CT>(dot, sh.scratch);
@@ -153,9 +160,8 @@ struct Mega {
         if (halo) ++halo_epoch;
         const bool pushed = halo && push_slots != 0u;
         if (tid < 32) {
-            // release: the CTA barrier above + this fence order every store of the CTA (at system scope when its
-            // rows went to peers) before the words below
-            if (pushed) fence_sys(); else fence_gpu();
+            // release: the CTA barrier above + this fence order every store of the CTA before the words below
+            if (release) fence_gpu();
             MegaSlot *s = &a.sync->slot[gen & (MEGA_RING - 1)][blockIdx.x];
             constexpr int NW = NV > 0 ? 2 * NV : 1;
             if (lane < NW) {
@@ -170,6 +176,9 @@ struct Mega {
                 st_ll_gpu(&s->w[lane], ll_pack(data, gen));
             }
             if (pushed) {
+                // rows that went to peers: order the NVLink stores at system scope, THEN raise this CTA's flag over there.
+                // After the slot words, so that the (latency-bound) reduction / the local neighbours do not wait for it.
+                fence_sys();
 #pragma unroll
                 for (int s2 = 0; s2 < MAX_RANKS - 1; ++s2)
                     if (lane == s2 && ((push_slots >> s2) & 1u)) st_flag_sys(a.push.hflag_dst[s2] + blockIdx.x, halo_epoch);
@@ -334,7 +343,7 @@ struct Mega {
     template <int NV>
     __device__ void reduce(double (&dot)[NV], int fin, bool tr = false)   // blocking sync point (MPI_Iallreduce + MPI_Wait)
     {
-        arrive<NV>(dot, false);
+        arrive<NV>(dot, false, false);
         if (tr) mark(11);
         if (a.comm.world > 1) ++red_epoch;
         finish<NV>(gen, fin, false, tr);
@@ -360,7 +369,7 @@ struct Mega {
     {
         if (after_spmv) {
             double d0[1] = {0.0};
-            arrive<0>(d0, false);
+            arrive<0>(d0, false, false);
             if (tid < RED_THREADS && tid < (int)gridDim.x && tid != (int)blockIdx.x) {
                 const unsigned long long *w = a.sync->slot[gen & (MEGA_RING - 1)][tid].w;
                 const unsigned long long t0 = globaltimer_ns();
@@ -488,22 +497,154 @@ struct Mega {
         if (tid == 0 && hi2 < row_hi) body<PH, Contig<1>>(a.v, hi2, c, dot);
     }
     // copy the rows of vector `id` that peers gather into their ghost regions (NVLink stores); the flag follows in arrive()
-    __device__ void push(int id)
+    __device__ void push(int id, int dst_id = -1)
     {
         if (a.comm.world == 1 || push_slots == 0u) return;
+        if (dst_id < 0) dst_id = id;
         nbar(1, CT);                                  // the rows being pushed are final
         PushDesc pd;
         pd.npeers = a.push.npeers; pd.fence_writers = 0;
         pd.src = a.vec_base + (long long)id * a.vstride;
 #pragma unroll
         for (int s = 0; s < MAX_RANKS - 1; ++s) {
-            pd.dst[s] = a.push.ghost0[s] + (long long)id * a.push.vstride[s];
+            pd.dst[s] = a.push.ghost0[s] + (long long)dst_id * a.push.vstride[s];
             pd.runs[s] = a.push.runs[s];
             pd.nruns[s] = ((push_slots >> s) & 1u) ? a.push.nruns[s] : 0;
         }
         push_chunk(pd, row_lo, row_hi, tid, CT);
     }
 
+    // ---------------------------------------------------------------- multi-GPU helpers ---------------------
+    // wait for the halo flags (epoch halo_epoch) of the peers' CTAs that fill the ghost slots in `senders`
+    __device__ void halo_wait(unsigned senders)
+    {
+        if (tid < 32) {
+            bool ok = true;
+            if (senders != 0u) {
+                const unsigned long long t0 = globaltimer_ns();
+                for (int s = 0; s < a.comm.world; ++s) {
+                    if (!((senders >> s) & 1u)) continue;
+                    const unsigned long long *f = a.sync->hflag[s];
+                    for (int i = lane; i < MEGA_MAX_CTAS; i += 32) {
+                        if (!((a.sync->pusher_mask[s][i >> 5] >> (i & 31)) & 1u)) continue;
+                        unsigned spins = 0;
+                        while (ld_relaxed_sys(&f[i]) < halo_epoch) {
+                            poll_pause(++spins);
+                            if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
+                        }
+                    }
+                }
+                fence_sys();
+            }
+            if (!__all_sync(0xffffffffu, ok) && lane == 0) fail();
+        }
+        nbar(1, CT);
+        if (sh.flags[3]) { if (tid == 0) { sh.sc.error = 1; sh.sc.done = 1; } nbar(1, CT); }
+    }
+    // releasing arrival + wait for EVERY CTA of this GPU (all == true) or for the CTAs owning the gathered columns
+    __device__ void sync_local(bool all)
+    {
+        double d0[1] = {0.0};
+        arrive<0>(d0, false, true);
+        if (!all) { wait_nbr(false); return; }
+        if (tid < RED_THREADS) {
+            if (tid < (int)gridDim.x && tid != (int)blockIdx.x) {
+                const unsigned long long *w = a.sync->slot[gen & (MEGA_RING - 1)][tid].w;
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned spins = 0;
+                while ((unsigned)(ld_ll_gpu(w) >> 32) != gen) {
+                    poll_pause(++spins);
+                    if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
+                }
+            }
+            nbar(2, RED_THREADS);
+            if (tid < 32) fence_gpu();                 // acquire (+ L1 invalidate) after ALL pollers are through
+        }
+        nbar(1, CT);
+        if (sh.flags[3]) { if (tid == 0) { sh.sc.error = 1; sh.sc.done = 1; } nbar(1, CT); }
+    }
+    // reduction whose arrival also carries a halo exchange: the pushers' flags go out right after the reduction words
+    template <int NV>
+    __device__ void reduce_halo(double (&dot)[NV], int fin, bool tr = false)
+    {
+        arrive<NV>(dot, true, false);
+        if (tr) mark(11);
+        ++red_epoch;
+        finish<NV>(gen, fin, false, tr);
+    }
+    // this CTA's share of the ghost slots, element-wise exactly like the owner's rows (same operands, same operation
+    // order -> bitwise the values the owner computes)
+    __device__ void ghost_q(const double *sv)                              // q = r - alpha s            solver.c:94
+    {
+        const double al = sh.sc.alpha;
+        double *r = a.v.r + a.ghost_off;
+        const double *sg = sv + a.ghost_off;
+        for (int i = gs_lo + tid; i < gs_hi; i += CT) r[i] = fma(-al, sg[i], r[i]);
+    }
+    __device__ void ghost_p(const double *sv)                              // p = r + beta (p - omega s)  solver.c:117-119
+    {
+        const double be = sh.sc.beta, nbo = -sh.sc.beta * sh.sc.omega;
+        double *p = a.v.p + a.ghost_off;
+        const double *r = a.v.r + a.ghost_off, *sg = sv + a.ghost_off;
+        for (int i = gs_lo + tid; i < gs_hi; i += CT) {
+            double t = be * p[i];
+            t = fma(1.0, r[i], t);
+            p[i] = fma(nbo, sg[i], t);
+        }
+    }
+    // ---------------------------------------------------------------- solver.c:86-127, several GPUs ---------
+    // Two halo exchanges per iteration instead of the reference's two allgathers -- and neither is waited for on its own:
+    // the boundary rows of s leave with the alpha reduction, those of the new r with the beta reduction (both are known
+    // before the reduction they ride on), and every rank advances its ghost copies of q and p itself with the
+    // recurrences q = r - alpha s, p = r + beta (p - omega s) applied to the ghost slots (bitwise what the owner
+    // computes).  So an iteration costs three NVLink-latency sync points, not five.  The ghost copy of s alternates
+    // between the ghost tails of two arena vectors (s, w): a peer may already push s of iteration k + 1 while this
+    // rank still applies s of iteration k to its ghost p.
+    __device__ void run_bicgstab_multi()
+    {
+        double d4[4], d2[2], d1[1], d0[1];
+        d0[0] = 0.0;
+        unsigned par = 0u;
+        while (true) {
+            mark(0);
+            d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
+            spmv<EPI_RH_Y>(a.v.p, a.v.s, d4);                               // s = A p, (r#,s)           :88-91
+            push(V_S, par ? V_W : V_S);
+            mark(1);
+            d1[0] = d4[0];
+            reduce_halo<1>(d1, FIN_BICG_ALPHA, true);                       // alpha                      :93
+            mark(2);
+            if (stop_now()) break;
+            const double *sv = par ? a.v.w : a.v.s;
+            halo_wait(gs_senders);
+            vec<PH_BICG_Q>(d0);                                             // q = r - alpha s            :94
+            ghost_q(sv);
+            mark(3);
+            sync_local(reads_ghost);
+            mark(4);
+            d4[0] = d4[1] = 0.0;
+            spmv<EPI_QY_YY>(a.v.r, a.v.y, d4);                              // y = A q, (q,y), (y,y)      :96-102
+            mark(5);
+            d2[0] = d4[0]; d2[1] = d4[1];
+            reduce<2>(d2, FIN_BICG_OMEGA);                                  // omega                      :104
+            mark(6);
+            d2[0] = d2[1] = 0.0;
+            vec<PH_BICG_XR>(d2);                                            // x, r, (r,r), (r#,r)        :105-114
+            push(V_R);
+            mark(7);
+            reduce_halo<2>(d2, FIN_BICG_BETA);                              // beta, k++, loop test       :116-120
+            mark(8);
+            if (stop_now()) break;
+            halo_wait(gs_senders);
+            vec<PH_BICG_P>(d0);                                             // p                          :117-119
+            ghost_p(sv);
+            mark(9);
+            sync_local(reads_ghost);
+            mark(10);
+            par ^= 1u;
+            ++trace_it;
+        }
+    }
     // ---------------------------------------------------------------- solver.c:86-127 -----------------------
     __device__ void run_bicgstab()
     {
@@ -716,6 +857,18 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
         if (a.comm.world > 1 && dep.z <= dep.w)
             for (int p = 0; p < a.comm.world; ++p)
                 if (a.ghost_first[p] <= dep.w && a.ghost_first[p + 1] > dep.z) m.need_senders |= 1u << p;
+        m.reads_ghost = a.comm.world > 1 && dep.z <= dep.w;
+        m.gs_lo = m.gs_hi = 0; m.gs_senders = 0u;
+        if (a.comm.world > 1) {
+            // ghost slots are shared out evenly (16-slot granules) over the CTAs
+            const int ng = a.ghost_first[a.comm.world];
+            const int chunk = ((ng + G - 1) / G + 15) & ~15;
+            m.gs_lo = min(ng, (int)blockIdx.x * chunk);
+            m.gs_hi = min(ng, m.gs_lo + chunk);
+            if (m.gs_hi > m.gs_lo)
+                for (int p = 0; p < a.comm.world; ++p)
+                    if (a.ghost_first[p] < m.gs_hi && a.ghost_first[p + 1] > m.gs_lo) m.gs_senders |= 1u << p;
+        }
         m.push_slots = 0u;
         if (a.comm.world > 1) {
             PushDesc pd;
@@ -726,14 +879,14 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
             }
         }
         nbar(1, CT);
-        if (a.comm.world > 1 && m.need_senders != 0u) {
-            // the vector the first SpMV gathers was pushed by the init kernels (kernel-per-phase protocol)
+        if (a.comm.world > 1 && (m.need_senders != 0u || m.gs_senders != 0u)) {
+            // the vectors the first phases read were pushed by the init kernels (kernel-per-phase protocol)
             if (tid < 32 && !halo_wait(a.comm, sh.sc.halo_epoch) && tid == 0) { sh.sc.error = 1; sh.sc.done = 1; }
             if (tid < 32) fence_sys();
             nbar(1, CT);
         }
         if (!m.stop_now()) {                                             // solver.c:86 before the first pass
-            if (a.method == 0) m.run_bicgstab();
+            if (a.method == 0) { if (a.comm.world > 1) m.run_bicgstab_multi(); else m.run_bicgstab(); }
             else if (a.method == 1) m.run_ca();
             else m.run_pipe(a.method == 3);
         }

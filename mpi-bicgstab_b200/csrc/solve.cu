@@ -167,6 +167,9 @@ struct Seq {
         vec(PH_PUSH, tail_none(), V_X);
         spmv(V_X, V_AX, tail_none());                                            // Ax = A x0
         vec(PH_BICG_INIT, tail_allreduce(FIN_BICG_INIT, 1), V_P);                // r, r#, p, (r,r)
+        // several GPUs, persistent kernel: it keeps ghost copies of r and p up to date itself (mega.cu: run_bicgstab_multi)
+        // and therefore starts from the ghost values of r0 as well (p0 = r0 was pushed just now)
+        if (m->world > 1 && c.cfg.mega && m->mega.ok && !c.prof_on) vec(PH_PUSH, tail_none(), V_R);
     }
     // ---- solver.c:88-120 -------------------------------------------------------------------------------
     void bicgstab_iter()
