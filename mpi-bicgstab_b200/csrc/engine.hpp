@@ -153,6 +153,10 @@ struct bicg_matrix {
     bicg::MegaPlan mega;             // persistent-kernel plan (mega.cu)
     bicg::MegaSync *d_msync = nullptr;
     bicg::MegaSync *peer_msync[bicg::MAX_RANKS] = {};
+    unsigned long long *d_ll = nullptr;                      // LL halo regions [3][ll_stride][2 words] (world > 1)
+    long long ll_stride = 0;
+    unsigned long long *peer_ll[bicg::MAX_RANKS] = {};
+    long long peer_ll_stride[bicg::MAX_RANKS] = {};
     int *d_ghost_first = nullptr;
     unsigned long long *d_trace = nullptr;   // BICG_MEGA_TRACE
     // ghost layout

@@ -482,7 +482,7 @@ constexpr int INLINE_RUNS = 48;      // receive runs that travel inside the boot
 struct ArenaHdr {
     cudaIpcMemHandle_t handle;
     unsigned long long arena_id;
-    long long vec_off, vstride, ghost_off, mail_off, hflag_off, msync_off;
+    long long vec_off, vstride, ghost_off, mail_off, hflag_off, msync_off, ll_off, ll_stride;
     int n_loc, n_ghost, n_runs, pad_;
     int runs[4 * INLINE_RUNS];
 };
@@ -589,6 +589,11 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     const size_t mail_off = off;  off = align(off + 2 * MAX_RANKS * sizeof(Mailbox));
     const size_t hflag_off = off; off = align(off + MAX_RANKS * sizeof(HaloFlag));
     const size_t msync_off = off; off = align(off + sizeof(MegaSync));
+    // LL halo of the multi-GPU BiCGStab loop (mega.cu: run_bicgstab_multi): three ghost-sized regions of 16-byte
+    // {lo | epoch, hi | epoch} pairs -- s (two parities) and r -- written by the peers, read by the ghost recurrences
+    const size_t ll_stride = (size_t)round_up(std::max(m->n_ghost, 1), 16);
+    const bool want_ll = m->world > 1 && (c.cfg.mega == 2 || c.cfg.mega_lanes > 0 || mega_lanes_for(m->mean_row) == 1);
+    const size_t ll_off = off;    off = align(off + (want_ll ? 3 * ll_stride * 16 : 0));
     m->arena_bytes = std::max<size_t>(off, (size_t)4 << 20);     // its own allocation granule: the IPC handle maps exactly this
     if (m->world > 1) {
         // exported through CUDA IPC: an allocation of its own (peers map exactly this one), parked and re-used by size
@@ -612,6 +617,8 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     m->d_mail = (Mailbox *)(m->arena + mail_off);
     m->d_hflag = (HaloFlag *)(m->arena + hflag_off);
     m->d_msync = (MegaSync *)(m->arena + msync_off);
+    m->d_ll = want_ll ? (unsigned long long *)(m->arena + ll_off) : nullptr;
+    m->ll_stride = (long long)ll_stride;
     BICG_CUDA(cudaStreamSynchronize(c.stream));            // arena zeroed before any peer may write into it
 
     lap("arena alloc + zero");
@@ -626,6 +633,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
         mine.handle = m->arena_handle; mine.arena_id = m->arena_id;
         mine.vec_off = (long long)vec_off; mine.vstride = m->vstride; mine.ghost_off = m->ghost_off;
         mine.mail_off = (long long)mail_off; mine.hflag_off = (long long)hflag_off; mine.msync_off = (long long)msync_off;
+        mine.ll_off = want_ll ? (long long)ll_off : -1; mine.ll_stride = (long long)ll_stride;
         mine.n_loc = m->n_loc; mine.n_ghost = m->n_ghost;
         const int my_cnt = (int)(m->recv_runs.size() / 4);
         mine.n_runs = my_cnt;
@@ -649,6 +657,8 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
             m->comm.mail[p] = (Mailbox *)((char *)m->peer_base[p] + all[(size_t)p].mail_off);
             m->comm.hflag[p] = (HaloFlag *)((char *)m->peer_base[p] + all[(size_t)p].hflag_off);
             m->peer_msync[p] = (MegaSync *)((char *)m->peer_base[p] + all[(size_t)p].msync_off);
+            m->peer_ll[p] = all[(size_t)p].ll_off >= 0 ? (unsigned long long *)((char *)m->peer_base[p] + all[(size_t)p].ll_off) : nullptr;
+            m->peer_ll_stride[p] = all[(size_t)p].ll_stride;
         }
         // receive lists of every rank: inline in the header, or (irregular matrices with many runs) a second round
         std::vector<int> cnts((size_t)m->world);
@@ -719,6 +729,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
                                       cudaMemcpyDefault, c.stream));
             BICG_CUDA(cudaStreamSynchronize(c.stream));          // `mask` is a stack buffer
         }
+        if (!m->d_ll) m->mega.ok = false;                 // the multi-GPU loops of the persistent kernel need the LL halo regions
         const int ok = m->mega.ok ? 1 : 0;
         for (int p = 0; p < m->world; ++p)
             BICG_CUDA(cudaMemcpyAsync(&m->peer_msync[p]->st.plan_ok[m->rank], &ok, sizeof(int), cudaMemcpyDefault, c.stream));

@@ -572,24 +572,69 @@ struct Mega {
         ++red_epoch;
         finish<NV>(gen, fin, false, tr);
     }
+    // Boundary rows of vector `id` -> LL region `region` of the peers that gather them: every element travels as one
+    // 16-byte pair of self-validating words {lo | epoch, hi | epoch} (dev.cuh), so the receiver needs neither a flag nor
+    // a system-scope fence on the sender's side -- it polls the words of the elements it consumes.
+    __device__ void push_ll(int id, int region, unsigned epoch)
+    {
+        if (push_slots == 0u) return;
+        nbar(1, CT);                                  // the rows being pushed are final
+        const double *src = a.vec_base + (long long)id * a.vstride;
+#pragma unroll
+        for (int s = 0; s < MAX_RANKS - 1; ++s) {
+            if (!((push_slots >> s) & 1u)) continue;
+            unsigned long long *dst = a.push.ll_dst[s] + 2ll * (long long)region * a.push.ll_stride[s];
+            const PushRun *runs = a.push.runs[s];
+            const int nr = a.push.nruns[s];
+            int lo = 0, hi = nr;                      // first run that ends after row_lo
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (runs[mid].src + runs[mid].len <= row_lo) lo = mid + 1; else hi = mid; }
+            for (int ri = lo; ri < nr; ++ri) {
+                const PushRun r = runs[ri];
+                if (r.src >= row_hi) break;
+                const int b = max(r.src, row_lo), e = min(r.src + r.len, row_hi);
+                for (int i = b + tid; i < e; i += CT) {
+                    unsigned long long w0, w1;
+                    ll_encode(src[i], epoch, w0, w1);
+                    st_ll_sys(dst + 2ll * (long long)(r.dst_off + (i - r.src)), w0, w1);
+                }
+            }
+        }
+    }
+    __device__ double ll_take(const unsigned long long *w, unsigned epoch, unsigned long long t0)
+    {
+        unsigned long long w0, w1;
+        unsigned spins = 0;
+        for (;;) {
+            ld_ll_sys(w, w0, w1);
+            if (ll_valid(w0, w1, epoch)) break;
+            poll_pause(++spins);
+            if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
+        }
+        return ll_decode(w0, w1);
+    }
     // this CTA's share of the ghost slots, element-wise exactly like the owner's rows (same operands, same operation
     // order -> bitwise the values the owner computes)
-    __device__ void ghost_q(const double *sv)                              // q = r - alpha s            solver.c:94
+    __device__ void ghost_q(int sregion, unsigned s_epoch)                 // q = r - alpha s            solver.c:94
     {
         const double al = sh.sc.alpha;
         double *r = a.v.r + a.ghost_off;
-        const double *sg = sv + a.ghost_off;
-        for (int i = gs_lo + tid; i < gs_hi; i += CT) r[i] = fma(-al, sg[i], r[i]);
+        const unsigned long long *sll = a.ll + 2ll * sregion * a.ll_stride;
+        const unsigned long long t0 = globaltimer_ns();
+        for (int i = gs_lo + tid; i < gs_hi; i += CT) r[i] = fma(-al, ll_take(sll + 2ll * i, s_epoch, t0), r[i]);
     }
-    __device__ void ghost_p(const double *sv)                              // p = r + beta (p - omega s)  solver.c:117-119
+    __device__ void ghost_p(int sregion, unsigned s_epoch, unsigned r_epoch)   // p = r + beta (p - omega s)  solver.c:117-119
     {
         const double be = sh.sc.beta, nbo = -sh.sc.beta * sh.sc.omega;
-        double *p = a.v.p + a.ghost_off;
-        const double *r = a.v.r + a.ghost_off, *sg = sv + a.ghost_off;
+        double *p = a.v.p + a.ghost_off, *r = a.v.r + a.ghost_off;
+        const unsigned long long *sll = a.ll + 2ll * sregion * a.ll_stride, *rll = a.ll + 2ll * 2 * a.ll_stride;
+        const unsigned long long t0 = globaltimer_ns();
         for (int i = gs_lo + tid; i < gs_hi; i += CT) {
+            const double rn = ll_take(rll + 2ll * i, r_epoch, t0);      // the owner's new r (pushed with the beta reduction)
+            const double sg = ll_take(sll + 2ll * i, s_epoch, t0);      // the same s the ghost q used (already validated)
             double t = be * p[i];
-            t = fma(1.0, r[i], t);
-            p[i] = fma(nbo, sg[i], t);
+            t = fma(1.0, rn, t);
+            p[i] = fma(nbo, sg, t);
+            r[i] = rn;                                                   // ghost r for the next q and for nothing else
         }
     }
     // ---------------------------------------------------------------- solver.c:86-127, several GPUs ---------
@@ -597,9 +642,11 @@ struct Mega {
     // the boundary rows of s leave with the alpha reduction, those of the new r with the beta reduction (both are known
     // before the reduction they ride on), and every rank advances its ghost copies of q and p itself with the
     // recurrences q = r - alpha s, p = r + beta (p - omega s) applied to the ghost slots (bitwise what the owner
-    // computes).  So an iteration costs three NVLink-latency sync points, not five.  The ghost copy of s alternates
-    // between the ghost tails of two arena vectors (s, w): a peer may already push s of iteration k + 1 while this
-    // rank still applies s of iteration k to its ghost p.
+    // computes).  So an iteration costs three NVLink-latency sync points, not five.  The boundary values travel as LL
+    // words (push_ll): no system-scope fence and no flag on the sender's side (a fence.sys after NVLink stores was
+    // measured at ~4.5 us), the consumer polls exactly the elements it needs.  The LL copy of s alternates between
+    // two regions: a peer may already push s of iteration k + 1 while this rank still applies s of iteration k to its
+    // ghost p; r needs one region (its next push follows a reduction that this rank enters after consuming it).
     __device__ void run_bicgstab_multi()
     {
         double d4[4], d2[2], d1[1], d0[1];
@@ -609,16 +656,15 @@ struct Mega {
             mark(0);
             d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
             spmv<EPI_RH_Y>(a.v.p, a.v.s, d4);                               // s = A p, (r#,s)           :88-91
-            push(V_S, par ? V_W : V_S);
+            const unsigned s_epoch = (unsigned)(++halo_epoch);
+            push_ll(V_S, (int)par, s_epoch);
             mark(1);
             d1[0] = d4[0];
-            reduce_halo<1>(d1, FIN_BICG_ALPHA, true);                       // alpha                      :93
+            reduce<1>(d1, FIN_BICG_ALPHA, true);                            // alpha                      :93
             mark(2);
             if (stop_now()) break;
-            const double *sv = par ? a.v.w : a.v.s;
-            halo_wait(gs_senders);
             vec<PH_BICG_Q>(d0);                                             // q = r - alpha s            :94
-            ghost_q(sv);
+            ghost_q((int)par, s_epoch);
             mark(3);
             sync_local(reads_ghost);
             mark(4);
@@ -630,14 +676,14 @@ struct Mega {
             mark(6);
             d2[0] = d2[1] = 0.0;
             vec<PH_BICG_XR>(d2);                                            // x, r, (r,r), (r#,r)        :105-114
-            push(V_R);
+            const unsigned r_epoch = (unsigned)(++halo_epoch);
+            push_ll(V_R, 2, r_epoch);
             mark(7);
-            reduce_halo<2>(d2, FIN_BICG_BETA);                              // beta, k++, loop test       :116-120
+            reduce<2>(d2, FIN_BICG_BETA);                                   // beta, k++, loop test       :116-120
             mark(8);
             if (stop_now()) break;
-            halo_wait(gs_senders);
             vec<PH_BICG_P>(d0);                                             // p                          :117-119
-            ghost_p(sv);
+            ghost_p((int)par, s_epoch, r_epoch);
             mark(9);
             sync_local(reads_ghost);
             mark(10);

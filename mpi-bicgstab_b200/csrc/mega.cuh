@@ -41,6 +41,8 @@ struct PushPlan {
     const PushRun *runs[MAX_RANKS - 1];
     int nruns[MAX_RANKS - 1];
     unsigned long long *hflag_dst[MAX_RANKS - 1];   // that rank's sync->hflag[this rank]: one flag per pushing CTA
+    unsigned long long *ll_dst[MAX_RANKS - 1];      // that rank's LL halo regions (region k at + k * 2 * ll_stride words)
+    long long ll_stride[MAX_RANKS - 1];             // ... its region length in elements
 };
 
 constexpr int MEGA_TRACE_ITERS = 256, MEGA_TRACE_SLOTS = 16;
@@ -66,6 +68,8 @@ struct MegaArgs {
     double *vec_base; long long vstride;   // arena vectors: vec(id) = vec_base + id * vstride
     VecPtrs v;
     PushPlan push;
+    const unsigned long long *ll;          // this rank's LL halo regions, [3][ll_stride] pairs: s (parity 0, 1), r
+    long long ll_stride;
     int method;                 // 0 bicgstab, 1 ca_bicgstab, 2 pipe_bicgstab, 3 pipe_bicgstab_rr
     int krr, nrr;
     unsigned long long *trace;  // optional [2][MEGA_TRACE_ITERS][MEGA_TRACE_SLOTS] globaltimer checkpoints (BICG_MEGA_TRACE)

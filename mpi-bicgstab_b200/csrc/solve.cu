@@ -104,7 +104,10 @@ struct Seq {
             a.push.runs[s] = m->d_push_runs[s];
             a.push.nruns[s] = m->push_nruns[s];
             a.push.hflag_dst[s] = &m->peer_msync[d]->hflag[m->rank][0];
+            a.push.ll_dst[s] = m->peer_ll[d];
+            a.push.ll_stride[s] = m->peer_ll_stride[d];
         }
+        a.ll = m->d_ll; a.ll_stride = m->ll_stride;
         a.method = method; a.krr = krr; a.nrr = nrr;
         a.trace = m->d_trace;
         int rc = launch_mega(m->mega.threads, m->mega.lanes, m->mega.grid, m->mega.smem, a, c.stream);

@@ -5,7 +5,7 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
  * and only as the checker.  The product (mpi-bicgstab_b200/) never links or calls this file.
  *
- * Parity pin: tests/test_oracle_vs_reference.py runs this restatement side by side with the
+ * Parity pin: tests/test_oracle_golden.py runs this restatement side by side with the
  * reference's own sources compiled in place (oracle/_ref/libref_strict.so, recipe in
  * oracle/Makefile) and requires bit-identical histories under strict IEEE evaluation
  * (-ffp-contract=off); tests/golden/ holds histories produced by that reference build
