@@ -333,3 +333,136 @@ void orc_spmv_ld(int n, const double *val, const unsigned *col, const unsigned *
         y[i] = (double)acc;
     }
 }
+
+/* ---- shifted_lopbicg_switching: shifted_switching_solver.c:260-602 ------------------------------
+ * Seed-switching shifted BiCGStab(1): one seed system (A + sigma[seed] I) x = b is iterated with BiCGStab; every
+ * other shift j is advanced from the seed's Krylov data with collinear-residual recurrences (eta, pi, zeta), and when the
+ * seed converges before the others the slowest remaining shift becomes the new seed (its scalars are re-derived from
+ * the archived alpha / beta / omega / pi history).  Restated line by line; the P-rank emulation of the dots and of the
+ * SpMV is the same as above.  x_set: sigma_len blocks of n (in: initial guess, reference drivers pass zeros), r: b in,
+ * seed residual out.  Returns the reference's return value (k, one more than the iterations performed);
+ * hist[k] = dot_r / dot_zero after iteration k, seed_out = final seed, stop_iter[j] = iteration at which shift j stopped
+ * (0 if it never did).  EPS 1e-12, MAX_ITER 1000 in the reference (:5-6). */
+int orc_shifted_lopbicg_switching(int n, const double *val, const unsigned *col, const unsigned *ptr, int P,
+                                  double *x_set, double *r, const double *sigma, int sigma_len, int seed,
+                                  double tol, int max_iter_opt, double *hist, int hist_cap, int *seed_out, int *stop_iter)
+{
+    orc_sys S; orc_sys_init(&S, n, val, col, ptr, P);
+    int i, j;
+    int k = 1, max_iter = max_iter_opt + 1, stop_count = 0;             /* :291-294 */
+    double max_zeta_pi, abs_zeta_pi;
+    int max_sigma = seed;
+    double *r_old = vnew(n), *r_hat = vnew(n), *s = vnew(n), *y = vnew(n), *q_copy = vnew(n);
+    double *p_set = (double *)calloc((size_t)n * (size_t)sigma_len, sizeof(double));           /* :304 */
+    double *alpha_set = vnew(sigma_len), *beta_set = vnew(sigma_len), *omega_set = vnew(sigma_len),
+           *eta_set = vnew(sigma_len), *zeta_set = vnew(sigma_len);
+    double *alpha_arch = vnew(max_iter), *beta_arch = vnew(max_iter), *omega_arch = vnew(max_iter);
+    double *pi_arch = (double *)calloc((size_t)max_iter * (size_t)sigma_len, sizeof(double));
+    char *stop_flag = (char *)calloc((size_t)sigma_len, 1);
+    double dot_r, dot_zero, rTr, rTs, qTq, qTy, rTr_old;
+#define PSET(jj) (p_set + (size_t)(jj) * (size_t)n)
+#define XSET(jj) (x_set + (size_t)(jj) * (size_t)n)
+#define PI(jj, kk) pi_arch[(size_t)(jj) * (size_t)max_iter + (size_t)(kk)]
+
+    rTr = orc_dot(&S, r, r);                                            /* :342 */
+    orc_copy(n, r, r_hat);                                              /* :344 */
+    for (i = 0; i < sigma_len; i++) {                                   /* :345-353 */
+        orc_copy(n, r, PSET(i));
+        alpha_set[i] = 1.0; beta_set[i] = 0.0; eta_set[i] = 0.0;
+        PI(i, 0) = 1.0; PI(i, 1) = 1.0;
+        zeta_set[i] = 1.0;
+    }
+    orc_copy(n, r, PSET(seed));                                         /* :354 */
+    dot_r = rTr; dot_zero = rTr; max_zeta_pi = 1.0;                     /* :357-359 */
+    alpha_arch[0] = 1.0; beta_arch[0] = 0.0;                            /* :361-362 */
+    if (hist && hist_cap > 0) hist[0] = 1.0;
+    if (stop_iter) for (j = 0; j < sigma_len; j++) stop_iter[j] = 0;
+
+    while (stop_count < sigma_len && k < max_iter) {                    /* :372 */
+        orc_copy(n, r, r_old);                                          /* :374 */
+        orc_spmv_sys(&S, PSET(seed), s);                                /* :377-384  s <- A p[seed]            */
+        orc_axpy(n, sigma[seed], PSET(seed), s);                        /* :386      s <- s + sigma[seed] p    */
+        rTs = orc_dot(&S, r_hat, s);                                    /* :387 */
+        alpha_arch[k] = rTr / rTs;                                      /* :390 */
+        orc_axpy(n, -alpha_arch[k], s, r);                              /* :391  q <- r - alpha s */
+        orc_copy(n, r, q_copy);                                         /* :392 */
+        orc_spmv_sys(&S, r, y);                                         /* :395-402  y <- A q */
+        orc_axpy(n, sigma[seed], r, y);                                 /* :404 */
+        qTq = orc_dot(&S, r, r);                                        /* :405 */
+        qTy = orc_dot(&S, r, y);                                        /* :406 */
+        omega_arch[k] = qTq / qTy;                                      /* :410 */
+        orc_axpy(n, alpha_arch[k], PSET(seed), XSET(seed));             /* :411 */
+        orc_axpy(n, omega_arch[k], r, XSET(seed));                      /* :412 */
+        orc_axpy(n, -omega_arch[k], y, r);                              /* :413 */
+        dot_r = orc_dot(&S, r, r);                                      /* :414 */
+        rTr_old = rTr;                                                  /* :415 */
+        rTr = orc_dot(&S, r_hat, r);                                    /* :416 */
+        beta_arch[k] = (alpha_arch[k] / omega_arch[k]) * (rTr / rTr_old);   /* :420 */
+        orc_scal(n, beta_arch[k], PSET(seed));                          /* :421 */
+        orc_axpy(n, 1.0, r, PSET(seed));                                /* :422 */
+        orc_axpy(n, -beta_arch[k] * omega_arch[k], s, PSET(seed));      /* :423 */
+
+        for (j = 0; j < sigma_len; j++) {                               /* :429-446 */
+            if (j == seed) continue;
+            if (stop_flag[j]) continue;
+            eta_set[j] = (beta_arch[k - 1] / alpha_arch[k - 1]) * alpha_arch[k] * eta_set[j]
+                       - (sigma[seed] - sigma[j]) * alpha_arch[k] * PI(j, k - 1);
+            PI(j, k) = eta_set[j] + PI(j, k - 1);
+            alpha_set[j] = (PI(j, k - 1) / PI(j, k)) * alpha_arch[k];
+            omega_set[j] = omega_arch[k] / (1.0 - omega_arch[k] * (sigma[seed] - sigma[j]));
+            orc_axpy(n, omega_set[j] / (PI(j, k) * zeta_set[j]), q_copy, XSET(j));
+            orc_axpy(n, alpha_set[j], PSET(j), XSET(j));
+            orc_axpy(n, omega_set[j] / (alpha_set[j] * zeta_set[j] * PI(j, k)), q_copy, PSET(j));
+            orc_axpy(n, -omega_set[j] / (alpha_set[j] * zeta_set[j] * PI(j, k - 1)), r_old, PSET(j));
+            zeta_set[j] = (1.0 - omega_arch[k] * (sigma[seed] - sigma[j])) * zeta_set[j];
+            beta_set[j] = (PI(j, k - 1) / PI(j, k)) * (PI(j, k - 1) / PI(j, k)) * beta_arch[k];
+            orc_scal(n, beta_set[j], PSET(j));
+            orc_axpy(n, 1.0 / (PI(j, k) * zeta_set[j]), r, PSET(j));
+        }
+
+        max_zeta_pi = 1.0;                                              /* :451-476 */
+        for (j = 0; j < sigma_len; j++) {
+            if (stop_flag[j]) continue;
+            if (j == seed) abs_zeta_pi = 1.0;
+            else abs_zeta_pi = fabs(1.0 / (zeta_set[j] * PI(j, k)));
+            if (abs_zeta_pi * abs_zeta_pi * dot_r <= tol * tol * dot_zero) {
+                stop_flag[j] = 1; stop_count++;
+                if (stop_iter) stop_iter[j] = k;
+            } else if (abs_zeta_pi > max_zeta_pi) {
+                max_zeta_pi = abs_zeta_pi; max_sigma = j;
+            }
+        }
+
+        if (stop_flag[seed] && stop_count < sigma_len) {                /* :490-527 seed switching */
+            for (i = 1; i <= k; i++) {
+                alpha_arch[i] = (PI(max_sigma, i - 1) / PI(max_sigma, i)) * alpha_arch[i];
+                beta_arch[i] = (PI(max_sigma, i - 1) / PI(max_sigma, i)) * (PI(max_sigma, i - 1) / PI(max_sigma, i)) * beta_arch[i];
+                omega_arch[i] = omega_arch[i] / (1.0 - omega_arch[i] * (sigma[seed] - sigma[max_sigma]));
+            }
+            orc_scal(n, 1.0 / (zeta_set[max_sigma] * PI(max_sigma, k)), r);
+            for (j = 0; j < sigma_len; j++) { eta_set[j] = 0.0; zeta_set[j] = 1.0; }
+            for (i = 1; i <= k; i++) {
+                for (j = 0; j < sigma_len; j++) {
+                    if (stop_flag[j]) continue;
+                    if (j == max_sigma) continue;
+                    eta_set[j] = (beta_arch[i - 1] / alpha_arch[i - 1]) * alpha_arch[i] * eta_set[j]
+                               - (sigma[max_sigma] - sigma[j]) * alpha_arch[i] * PI(j, i - 1);
+                    PI(j, i) = eta_set[j] + PI(j, i - 1);
+                    zeta_set[j] = (1.0 - omega_arch[i] * (sigma[max_sigma] - sigma[j])) * zeta_set[j];
+                }
+            }
+            seed = max_sigma;
+        }
+        if (hist && k < hist_cap) hist[k] = dot_r / dot_zero;
+        k++;                                                            /* :537 */
+    }
+    if (seed_out) *seed_out = seed;
+    free(r_old); free(r_hat); free(s); free(y); free(q_copy); free(p_set);
+    free(alpha_set); free(beta_set); free(omega_set); free(eta_set); free(zeta_set);
+    free(alpha_arch); free(beta_arch); free(omega_arch); free(pi_arch); free(stop_flag);
+    orc_sys_free(&S);
+#undef PSET
+#undef XSET
+#undef PI
+    return k;
+}

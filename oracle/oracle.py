@@ -55,6 +55,9 @@ def lib():
         L.orc_spmv_ld.argtypes = [C.c_int, _dp, _up, _up, _dp, _dp]
         L.orc_ddot.restype = C.c_double
         L.orc_ddot.argtypes = [C.c_int, _dp, _dp]
+        L.orc_shifted_lopbicg_switching.restype = C.c_int
+        L.orc_shifted_lopbicg_switching.argtypes = [C.c_int, _dp, _up, _up, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_int,
+                                                    _dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_daxpy.restype = None
         L.orc_daxpy.argtypes = [C.c_int, C.c_double, _dp, _dp]
         L.orc_dscal.restype = None
@@ -187,6 +190,48 @@ def ref_solve(method, n, ptr, col, val, b, x0=None, tol=1e-15, max_iter=1000, kr
     res = np.array([L.orc_ref_hist_res(i) for i in range(cnt)])
     return {"iters": it, "x": x, "r": r, "res": res, "final_res": L.orc_ref_final_res(),
             "avg_time": L.orc_ref_avg_time(), "total_time": L.orc_ref_total_time()}
+
+
+def shifted_solve(n, ptr, col, val, b, sigma, seed, P=1, tol=1e-12, max_iter=1000):
+    """Restated shifted_lopbicg_switching (shifted_switching_solver.c:260-602).  Returns dict(ret, iters, x (sigma_len x n), r, hist,
+    seed, stop_iter)."""
+    ptr, col, val = _csr(ptr, col, val)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    x = np.zeros((sigma.size, n))
+    r = np.array(b, dtype=np.float64)
+    hist = np.full(max_iter + 2, np.nan)
+    seed_out = C.c_int(seed)
+    stop_iter = (C.c_int * sigma.size)()
+    ret = lib().orc_shifted_lopbicg_switching(n, _p(val, _dp), _p(col, _up), _p(ptr, _up), P, _p(x, _dp), _p(r, _dp), _p(sigma, _dp),
+                                              sigma.size, seed, tol, max_iter, _p(hist, _dp), hist.size, C.byref(seed_out), stop_iter)
+    return {"ret": ret, "iters": ret - 1, "x": x, "r": r, "hist": hist[:ret], "seed": seed_out.value, "stop_iter": np.array(stop_iter[:])}
+
+
+def ref_shifted_solve(n, ptr, col, val, b, sigma, seed, tol=1e-12, max_iter=1000, flavour="strict"):
+    """The reference's own shifted_lopbicg_switching() (P = 1) called in-process on an in-memory CSR."""
+    L = ref_lib(flavour)
+    ptr, col, val = _csr(ptr, col, val)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    D, O, info = _RefCSR(), _RefCSR(), _RefInfo()
+    D.val, D.col, D.ptr = _p(val, _dp), _p(col, _up), _p(ptr, _up)
+    D.nz, D.rows, D.cols = int(ptr[-1]), n, n
+    zero_ptr = np.zeros(n + 1, dtype=np.uint32)
+    one_d, one_u = np.zeros(1), np.zeros(1, dtype=np.uint32)
+    O.val, O.col, O.ptr = _p(one_d, _dp), _p(one_u, _up), _p(zero_ptr, _up)
+    O.nz, O.rows, O.cols = 0, n, n
+    rc = (C.c_int * 1)(n)
+    ds = (C.c_int * 1)(0)
+    info.nz, info.rows, info.cols, info.code = int(ptr[-1]), n, n, b"MCRG"
+    info.recvcounts, info.displs = C.cast(rc, C.POINTER(C.c_int)), C.cast(ds, C.POINTER(C.c_int))
+    x = np.zeros((sigma.size, n))
+    r = np.array(b, dtype=np.float64)
+    L.orc_ref_config(tol, max_iter, 1, 1)
+    L.orc_ref_hist_reset()
+    L.shifted_lopbicg_switching.restype = C.c_int
+    ret = L.shifted_lopbicg_switching(C.byref(D), C.byref(O), C.byref(info), _p(x, _dp), _p(r, _dp), _p(sigma, _dp), int(sigma.size), int(seed))
+    cnt = L.orc_ref_hist_count()
+    res = np.array([L.orc_ref_hist_res(i) for i in range(cnt)])
+    return {"ret": ret, "iters": ret - 1, "x": x, "r": r, "res": res}
 
 
 def write_csr_bin(path, n, ptr, col, val):

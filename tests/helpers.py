@@ -12,6 +12,25 @@ METHODS = ["bicgstab", "ca_bicgstab", "pipe_bicgstab", "pipe_bicgstab_rr"]
 RR = dict(krr=10, nrr=3)
 
 
+# shifted family: (name, kind, g, p0, number of shifts, shift scale, seed index); sigma_j = (j + 1) * scale.
+# The reference drivers use scale = 0.01 / L and seed 0 (main_shifted.c:95-99); the large-scale cases make the seed (the most
+# diagonally dominant system) converge first, which exercises seed switching (shifted_switching_solver.c:490-527).
+SHIFTED_CASES = [
+    ("sh_stencil15_g12_L5", "stencil15", 12, 14.0, 5, 0.01 / 5, 0),
+    ("sh_convdiff_g40_L6_switch", "convdiff", 40, 1.5, 6, 0.8, 5),
+    ("sh_stencil15_g12_L4_switch", "stencil15", 12, 14.0, 4, 2.0, 3),
+    ("sh_laplace5_g37_L16", "laplace5", 37, 0.0, 16, 0.01 / 16, 0),
+]
+
+
+def shifted_problem(O, n, ptr, col, val, L, scale, seed):
+    """sigma and b = (A + sigma[seed] I) 1 as main_shifted.c:95-114 builds them."""
+    sigma = (np.arange(L) + 1) * scale
+    b = O.spmv(n, ptr, col, val, np.ones(n))
+    O.daxpy(sigma[seed], np.ones(n), b)
+    return sigma, b
+
+
 def global_csr(B, kind, g, p0, seed=12345):
     blk = B.gen_block(kind, g, p0, seed)
     ptr, col, val = B.block_to_global_csr(blk)

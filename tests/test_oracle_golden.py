@@ -83,3 +83,41 @@ def test_manufactured_solution(B, O):
         kw = RR if method.endswith("rr") else {}
         o = O.solve(method, n, ptr, col, val, b, tol=1e-12, max_iter=500, **kw)
         assert np.abs(o["x"] - 1).max() < 1e-8
+
+
+# ---- shifted family --------------------------------------------------------------------------
+from helpers import SHIFTED_CASES, shifted_problem
+
+
+@pytest.fixture(scope="module")
+def gold_shifted():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_shifted.npz"))
+
+
+@pytest.mark.parametrize("name,kind,g,p0,L,scale,seed", SHIFTED_CASES)
+def test_shifted_oracle_reproduces_reference_bitwise(B, O, gold_shifted, name, kind, g, p0, L, scale, seed):
+    """orc_shifted_lopbicg_switching vs the golden outputs of the reference's own shifted_lopbicg_switching
+    (shifted_switching_solver.c:260-602, strict build): same return value, bit-identical x_j for every shift, r and history."""
+    blk, n, ptr, col, val = global_csr(B, kind, g, p0)
+    sigma, b = shifted_problem(O, n, ptr, col, val, L, scale, seed)
+    o = O.shifted_solve(n, ptr, col, val, b, sigma, seed, tol=1e-12, max_iter=1000)
+    assert o["ret"] == int(gold_shifted[name + "|ret"])
+    assert np.array_equal(o["x"], gold_shifted[name + "|x"])
+    assert np.array_equal(o["r"], gold_shifted[name + "|r"])
+    assert np.array_equal(np.sqrt(o["hist"][1:]), gold_shifted[name + "|res"])
+    if "switch" in name:
+        assert o["seed"] != seed                                   # the seed-switching branch really ran
+    for j in range(L):                                             # and every shifted system is solved
+        res = O.spmv(n, ptr, col, val, o["x"][j]) + sigma[j] * o["x"][j] - b
+        assert np.linalg.norm(res) <= 1e-10 * np.linalg.norm(b)
+
+
+def test_shifted_oracle_against_compiled_reference_live(B, O):
+    if not O.have_ref("libref_strict.so"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    name, kind, g, p0, L, scale, seed = SHIFTED_CASES[1]
+    blk, n, ptr, col, val = global_csr(B, kind, g, p0)
+    sigma, b = shifted_problem(O, n, ptr, col, val, L, scale, seed)
+    o = O.shifted_solve(n, ptr, col, val, b, sigma, seed)
+    r = O.ref_shifted_solve(n, ptr, col, val, b, sigma, seed)
+    assert o["ret"] == r["ret"] and np.array_equal(o["x"], r["x"]) and np.array_equal(o["r"], r["r"])
