@@ -736,7 +736,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
         BICG_CUDA(cudaStreamSynchronize(c.stream));
     }
     if (c.cfg.mega_trace) {
-        const size_t tb = (size_t)2 * MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS * sizeof(unsigned long long);
+        const size_t tb = ((size_t)2 * MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS + (size_t)2 * MEGA_MAX_CTAS) * sizeof(unsigned long long);
         m->d_trace = (decltype(m->d_trace))c.dev_alloc(tb);
         BICG_CUDA(cudaMemset(m->d_trace, 0, tb));
     }

@@ -130,6 +130,7 @@ struct Mega {
     int gs_lo, gs_hi;             // ghost slots this CTA keeps up to date itself (multi-GPU bicgstab: redundant recurrences)
     unsigned gs_senders;          // ranks that fill those slots
     bool reads_ghost;             // this CTA's rows gather ghost columns
+    bool is_reducer;              // N > 1: the CTA that adds up this GPU's slots and posts them to the peers' mailboxes
     size_t stage_bytes;
     int trace_it, trace_who;
 
@@ -137,6 +138,11 @@ struct Mega {
 
     __device__ bool stop_now() const { return sh.sc.done != 0 || sh.sc.error != 0; }
     __device__ void fail() { sh.flags[3] = 1; }
+    // one iteration's alpha sync seen by EVERY CTA: [G][2] = arrival, release (globaltimer, per GPU)
+    __device__ void snap(int which)
+    {
+        if (a.snap && tid == 0 && sh.sc.k == a.snap_iter) a.snap[2 * blockIdx.x + which] = globaltimer_ns();
+    }
     __device__ void mark(int slot)
     {
         if (a.trace && trace_who >= 0 && tid == 0 && trace_it < MEGA_TRACE_ITERS)
@@ -327,7 +333,7 @@ struct Mega {
     {
         if (a.comm.world == 1) { local_reduce<NV>(g); if (tr) mark(12); }
         else {
-            if (blockIdx.x == 0 && !posted) { local_reduce<NV>(g); if (tr) mark(12); if (tid < 32) post_mail<NV>(); if (tr) mark(13); }
+            if (is_reducer && !posted) { local_reduce<NV>(g); if (tr) mark(12); if (tid < 32) post_mail<NV>(); if (tr) mark(13); }
             if (tid < 32) mail_reduce<NV>();
             if (tr) mark(14);
         }
@@ -344,9 +350,10 @@ struct Mega {
     __device__ void reduce(double (&dot)[NV], int fin, bool tr = false)   // blocking sync point (MPI_Iallreduce + MPI_Wait)
     {
         arrive<NV>(dot, false, false);
-        if (tr) mark(11);
+        if (tr) { mark(11); snap(0); }
         if (a.comm.world > 1) ++red_epoch;
         finish<NV>(gen, fin, false, tr);
+        if (tr) snap(1);
     }
     template <int NV>
     __device__ void post(double (&dot)[NV], bool halo)          // MPI_Iallreduce (+ the halo of the SpMV that hides it)
@@ -356,7 +363,7 @@ struct Mega {
         posted_gen = gen;
         if (a.comm.world > 1) {
             ++red_epoch;
-            if (blockIdx.x == 0) { local_reduce<NV>(gen); if (tid < 32) post_mail<NV>(); }
+            if (is_reducer) { local_reduce<NV>(gen); if (tid < 32) post_mail<NV>(); }
         }
         wait_nbr(halo);
     }
@@ -904,6 +911,9 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
             for (int p = 0; p < a.comm.world; ++p)
                 if (a.ghost_first[p] <= dep.w && a.ghost_first[p + 1] > dep.z) m.need_senders |= 1u << p;
         m.reads_ghost = a.comm.world > 1 && dep.z <= dep.w;
+        // the reducer sits in the middle of the row range: on banded matrices the CTAs at the ends are busy pushing boundary
+        // rows over NVLink (slow per SM) right before the reductions, and everybody would wait for them twice
+        m.is_reducer = (int)blockIdx.x == G / 2;
         m.gs_lo = m.gs_hi = 0; m.gs_senders = 0u;
         if (a.comm.world > 1) {
             // ghost slots are shared out evenly (16-slot granules) over the CTAs

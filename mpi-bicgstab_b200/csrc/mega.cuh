@@ -72,6 +72,8 @@ struct MegaArgs {
     long long ll_stride;
     int method;                 // 0 bicgstab, 1 ca_bicgstab, 2 pipe_bicgstab, 3 pipe_bicgstab_rr
     int krr, nrr;
+    unsigned long long *snap;   // optional [grid][2]: arrival / release of the alpha sync of iteration snap_iter, every CTA
+    int snap_iter;
     unsigned long long *trace;  // optional [2][MEGA_TRACE_ITERS][MEGA_TRACE_SLOTS] globaltimer checkpoints (BICG_MEGA_TRACE)
 };
 

@@ -110,6 +110,8 @@ struct Seq {
         a.ll = m->d_ll; a.ll_stride = m->ll_stride;
         a.method = method; a.krr = krr; a.nrr = nrr;
         a.trace = m->d_trace;
+        a.snap = m->d_trace ? m->d_trace + (size_t)2 * MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS : nullptr;
+        a.snap_iter = 50;
         int rc = launch_mega(m->mega.threads, m->mega.lanes, m->mega.grid, m->mega.smem, a, c.stream);
         if (rc) {
             // e.g. the grid cannot be co-resident because something else holds SMs.  Single rank: not an error, the
@@ -411,6 +413,23 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
             snprintf(line + o, sizeof(line) - o, " || alpha sync: arrive %.2f local %.2f post %.2f mail %.2f\n", sub[0] / std::max(1, iters - 1) * 1e-3,
                      sub[1] / std::max(1, iters - 1) * 1e-3, sub[2] / std::max(1, iters - 1) * 1e-3, sub[3] / std::max(1, iters - 1) * 1e-3);
             fputs(line, stderr);
+        }
+        {   // the alpha sync of iteration 50 as every CTA saw it: spread of the arrivals, and how long after the LAST arrival
+            // (this GPU's) the CTAs were released
+            std::vector<unsigned long long> sn((size_t)2 * MEGA_MAX_CTAS);
+            BICG_CUDA(cudaMemcpy(sn.data(), m->d_trace + (size_t)2 * MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS, sn.size() * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost));
+            unsigned long long a_min = ~0ull, a_max = 0, r_min = ~0ull, r_max = 0; int last = -1;
+            for (int g = 0; g < m->mega.grid; ++g) {
+                if (!sn[2 * (size_t)g]) continue;
+                if (sn[2 * (size_t)g] > a_max) { a_max = sn[2 * (size_t)g]; last = g; }
+                a_min = std::min(a_min, sn[2 * (size_t)g]);
+                r_min = std::min(r_min, sn[2 * (size_t)g + 1]); r_max = std::max(r_max, sn[2 * (size_t)g + 1]);
+            }
+            if (last >= 0)
+                fprintf(stderr, "[bicg mega snap r%d] alpha sync @ iteration 50: arrivals spread %.2f us (last: CTA %d), first release %.2f us / last release "
+                                "%.2f us after the last local arrival\n", m->rank, (double)(a_max - a_min) * 1e-3, last,
+                        ((double)r_min - (double)a_max) * 1e-3, ((double)r_max - (double)a_max) * 1e-3);
         }
     }
 
