@@ -71,6 +71,13 @@ int pipe_bicgstab_rr(CSR_Matrix *A_loc_diag, CSR_Matrix *A_loc_offd, INFO_Matrix
 
 #endif /* MATRIX_H */
 
+/* shifted_switching_solver.h:12 (shifted_switching_solver.c:260-602): seed-switching shifted BiCGStab for (A + sigma_j I) x_j = b.
+ * x_loc_set: sigma_len blocks of n_loc doubles (initial guesses in, solutions out); r_loc: b in, seed residual out; returns the
+ * reference's k (iterations performed + 1).  EPS / MAX_ITER of the reference (1e-12 / 1000, :5-6) = BICG_SHIFT_TOL /
+ * BICG_SHIFT_MAX_ITER.  Not needed by main.c; it is what main_shifted.c / main_repeat.c call. */
+int shifted_lopbicg_switching(CSR_Matrix *A_loc_diag, CSR_Matrix *A_loc_offd, INFO_Matrix *A_info, double *x_loc_set,
+                              double *r_loc, double *sigma, int sigma_len, int seed);
+
 /* ------------------------------------------------------------------------------------------------
  * Part 2 -- extensions
  * ---------------------------------------------------------------------------------------------- */
@@ -129,6 +136,11 @@ typedef struct {
  * case they are device pointers (same in/out meaning as Part 1).  krr/nrr only for BICG_METHOD_PIPE_RR. */
 int bicg_solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, int device_vectors,
                bicg_stats *stats);
+
+/* shifted_lopbicg_switching on a resident matrix; bicg_last_shift_info: the seed the last shifted solve ended with and the
+ * iteration at which every shift stopped (returns sigma_len). */
+int bicg_shifted_solve(bicg_matrix *m, double *x_set, double *r, const double *sigma, int sigma_len, int seed, bicg_stats *stats);
+int bicg_last_shift_info(int *seed, int *stop_iter, int cap);
 
 /* y_loc = A x_loc on a resident matrix (host pointers) -- the kernel behind MPI_csr_spmv_ovlap. */
 int bicg_spmv(bicg_matrix *m, const double *x_loc, double *y_loc);

@@ -226,6 +226,21 @@ def solve(method, blk, x_loc, r_loc, krr=0, nrr=0):
     return {"bicgstab": bicgstab, "ca_bicgstab": ca_bicgstab, "pipe_bicgstab": pipe_bicgstab}[method](blk, x_loc, r_loc)
 
 
+def shifted_lopbicg_switching(blk, x_set, r_loc, sigma, seed):
+    """shifted_switching_solver.h:12.  x_set: (sigma_len, n_loc) C-contiguous; returns the reference's k (iterations + 1)."""
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    assert x_set.dtype == np.float64 and x_set.flags["C_CONTIGUOUS"] and x_set.shape == (sigma.size, blk.n_loc)
+    return lib.shifted_lopbicg_switching(C.byref(blk.diag), C.byref(blk.offd), C.byref(blk.info), _dptr(x_set), _vec(r_loc, blk.n_loc),
+                                         _dptr(sigma), int(sigma.size), int(seed))
+
+
+def last_shift_info(sigma_len):
+    seed = C.c_int()
+    stop = (C.c_int * sigma_len)()
+    lib.bicg_last_shift_info(C.byref(seed), stop, sigma_len)
+    return seed.value, np.array(stop[:])
+
+
 # ---- extensions ------------------------------------------------------------------------------------------
 def set_option(key, value):
     if lib.bicg_set_option(str(key).encode(), str(value).encode()) != 0:

@@ -66,6 +66,23 @@ int pipe_bicgstab_rr(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_
     return run_reference_entry(BICG_METHOD_PIPE_RR, D, O, info, x_loc, r_loc, krr, nrr);
 }
 
+// shifted_switching_solver.h:12 -- same prototype, host pointers: x_loc_set holds sigma_len blocks of n_loc (initial guesses in,
+// solutions out), r_loc b in / seed residual out.  Returns the reference's k (iterations + 1).
+int shifted_lopbicg_switching(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_loc_set, double *r_loc, double *sigma,
+                              int sigma_len, int seed)
+{
+    if (info->cols != info->rows) {                      // shifted_switching_solver.c:268-271
+        printf("Error: matrix is not square.\n");
+        exit(1);
+    }
+    Context &c = ctx();
+    c.ensure();
+    bicg_matrix *m = matrix_get_cached(D, O, info, nullptr);
+    const int k = shifted_solve(m, x_loc_set, r_loc, sigma, sigma_len, seed, c.cfg.shift_tol, c.cfg.shift_max_iter);
+    if (!c.cfg.cache) matrix_destroy(m);
+    return k;
+}
+
 void MPI_csr_spmv_ovlap(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_loc, double *x, double *y_loc)
 {
     Context &c = ctx();
@@ -135,6 +152,21 @@ int bicg_solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nr
     return solve(m, method, x, r, krr, nrr, device_vectors, stats);
 }
 int bicg_spmv(bicg_matrix *m, const double *x_loc, double *y_loc) { return spmv_host(m, x_loc, y_loc, nullptr); }
+int bicg_shifted_solve(bicg_matrix *m, double *x_set, double *r, const double *sigma, int sigma_len, int seed, bicg_stats *stats)
+{
+    Context &c = ctx();
+    const int k = shifted_solve(m, x_set, r, sigma, sigma_len, seed, c.cfg.shift_tol, c.cfg.shift_max_iter);
+    if (stats) *stats = c.last_stats;
+    return k;
+}
+int bicg_last_shift_info(int *seed, int *stop_iter, int cap)
+{
+    Context &c = ctx();
+    if (seed) *seed = c.last_shift_seed;
+    const int n = (int)c.last_shift_stop.size();
+    for (int i = 0; i < n && i < cap; ++i) stop_iter[i] = c.last_shift_stop[(size_t)i];
+    return n;
+}
 int bicg_spmv_time(bicg_matrix *m, int reps, double *ms, double *bytes) { return spmv_time(m, reps, ms, bytes); }
 
 int bicg_last_history(double *out, int cap)

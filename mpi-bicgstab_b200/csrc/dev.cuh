@@ -66,6 +66,7 @@ enum Fin : int {
     FIN_CAPIPE_INIT,   // tot0=(r,w) -> alpha, beta=0, omega=0, test   solver.c:206-213
     FIN_OMEGA2,        // tot0=(q,y) tot1=(y,y) -> omega               solver.c:227-232 / 363-369
     FIN_CAPIPE_END,    // tot0..3=(r#,r),(r#,w),(r#,s),(r#,z) tot4=(r,r) -> beta, alpha, k++, test   solver.c:240-253
+    FIN_STORE_PEND,    // reduced values -> Scalars::pend[] (the shifted solver's own scalar kernels take it from there)
 };
 
 // what the tail does with the locally reduced dots
@@ -381,6 +382,9 @@ __device__ __forceinline__ void finalize(int fin, Scalars *s, double *hist, cons
         s->k += 1;
         BICG_HIST(s->k) = s->dot_r / s->dot_zero;
         loop_test(s);
+        break;
+    case FIN_STORE_PEND:
+        for (int k = 0; k < MAX_DOTS; ++k) s->pend[k] = t[k];
         break;
     default: break;
     }

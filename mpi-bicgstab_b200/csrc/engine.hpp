@@ -48,6 +48,8 @@ struct Config {
     int device = -1;
     int halo_gap = 64;
     int verbose = 0;
+    double shift_tol = 1.0e-12;  // EPS of the shifted solvers (shifted_switching_solver.c:5)
+    int shift_max_iter = 1000;   // their MAX_ITER (:6)
     int peer_timeout_s = 20;     // bound of device-side waits for peers / other CTAs (then: error + exit(1))
     int fence_writers = 0;       // 1: every thread that stored to a peer also fences at system scope itself (debug aid;
                                  // the CTA barrier + one system fence per CTA is sufficient and much cheaper)
@@ -78,6 +80,8 @@ struct Context {
     // results of the last solve
     std::vector<double> last_hist;
     bicg_stats last_stats{};
+    std::vector<int> last_shift_stop;     // shifted solver: iteration at which every shift stopped
+    int last_shift_seed = 0;              // ... and the seed it ended with
     // host-pointer keyed cache of uploaded matrices
     std::map<const void *, bicg_matrix *> cache;
     std::map<TuneKey, TuneVal> tuned;     // SpMV autotune winners by matrix shape
@@ -210,6 +214,8 @@ int  solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, i
 int  spmv_host(bicg_matrix *m, const double *x_loc, double *y_loc, double *x_full_or_null);
 int  spmv_time(bicg_matrix *m, int reps, double *ms, double *bytes);
 void print_reference_lines(const bicg_stats &st, const std::vector<double> &hist);
+// shifted.cu
+int  shifted_solve(bicg_matrix *m, double *x_set, double *r, const double *sigma, int sigma_len, int seed, double tol, int max_iter);
 // helpers shared by matrix.cu / solve.cu
 SpmvArgs make_spmv_args(const bicg_matrix *m, const SpmvPlan &p, int x_id, int y_id);
 void launch_spmv_plan(const bicg_matrix *m, const SpmvPlan &p, const SpmvArgs &a, int prof_class = 0);

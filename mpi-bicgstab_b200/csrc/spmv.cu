@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(CTHREADS + 32, 1) spmv_ws_kernel(const __grid_
             }
             acc = lanes_sum<LANES>(acc);
             if (valid && lane == 0) {
+                if (a.shift_sigma) acc = fma(*a.shift_sigma, ld_coherent(x + row), acc);     // s += sigma p (daxpy after the SpMV)
                 a.y[row] = acc;
                 const int ro = row - h.rowa;
 #pragma unroll
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(256) spmv_rowsplit_kernel(const __grid_constan
         for (; j < pe; j += LANES) acc = fma(val[j], ld_coherent(x + col[j]), acc);
         acc = lanes_sum<LANES>(acc);
         if (valid && lane == 0) {
+            if (a.shift_sigma) acc = fma(*a.shift_sigma, ld_coherent(x + row), acc);
             a.y[row] = acc;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

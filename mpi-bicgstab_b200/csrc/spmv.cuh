@@ -32,6 +32,7 @@ struct SpmvArgs {
     double       *y;            // output, own rows
     EpiArgs epi;
     int wait_halo;              // 1: x's ghost part is filled by peers; wait for their halo flags first
+    const double *shift_sigma;  // not null: y = A x + (*shift_sigma) x  (shifted systems, shifted_switching_solver.c:386, 404)
 };
 
 // kind 0: warp-specialised TMA tile kernel, kind 1: row-split kernel.  threads (consumer threads) only matters for kind 0.

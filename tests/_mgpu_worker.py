@@ -59,6 +59,26 @@ def main():
             if rank == 0:
                 print(f"[mgpu {world}] {kind:10s} {method:17s} mega={mega} {it:4d} it (oracle {ref['iters']}), launches {st['kernel_launches']}", flush=True)
         dm.destroy()
+    # shifted family: one seed-switching case, every rank checks its slice of every x_j against the oracle's P-rank emulation
+    from helpers import SHIFTED_CASES, shifted_problem
+    name, kind, g, p0, L, scale, seed = SHIFTED_CASES[1]
+    blk = B.gen_block(kind, g, p0, rank=rank, world=world)
+    n, nloc, lo = blk.n, blk.n_loc, int(blk.displs[rank])
+    ptr, col, val = B.block_to_global_csr(B.gen_block(kind, g, p0))
+    sigma = (np.arange(L) + 1) * scale
+    bg = O.spmv(n, ptr, col, val, np.ones(n), P=world)
+    O.daxpy(sigma[seed], np.ones(n), bg)
+    ref = O.shifted_solve(n, ptr, col, val, bg, sigma, seed, P=world, tol=1e-12, max_iter=1000)
+    B.set_options(shift_tol=1e-12, shift_max_iter=1000)
+    xs = np.zeros((L, nloc)); rs = np.ascontiguousarray(bg[lo:lo + nloc])
+    ret = B.shifted_lopbicg_switching(blk, xs, rs, sigma, seed)
+    end_seed, stop = B.last_shift_info(L)
+    assert abs(ret - ref["ret"]) <= 2 and end_seed == ref["seed"], (ret, ref["ret"], end_seed, ref["seed"])
+    for j in range(L):
+        assert np.abs(xs[j] - ref["x"][j][lo:lo + nloc]).max() <= 1e-8 * np.abs(ref["x"][j]).max(), ("shifted", j, rank)
+    if rank == 0:
+        print(f"[mgpu {world}] shifted_lopbicg_switching {name}: ret {ret} (oracle {ref['ret']}), final seed {end_seed}, stops {stop}", flush=True)
+
     # the reference-facing host-pointer entry point, collectively
     blk = B.gen_block("stencil15", 14, 14.0, rank=rank, world=world)
     B.set_options(tol=TOL, max_iter=600)
