@@ -256,7 +256,8 @@ struct Mega {
 #pragma unroll
                     for (int k = 0; k < NV; ++k) { ld_ll_gpu2(w + 2 * k, w0[k], w1[k]); all = all && ll_valid(w0[k], w1[k], g); }
                     if (all) break;
-                    poll_pause(++spins);
+                    ++spins;
+                    if (a.comm.world == 1) poll_pause(spins);        // N > 1: only the reducer CTA polls the slots -- no crowd, no pause
                     if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
                 }
 #pragma unroll
@@ -313,7 +314,7 @@ struct Mega {
 #pragma unroll
                 for (int k = 0; k < NV; ++k) { ld_ll_sys(w + 2 * k, w0[k], w1[k]); all = all && ll_valid(w0[k], w1[k], red_epoch); }
                 if (all) break;
-                poll_pause(++spins);
+                if (++spins > 4u) __nanosleep(48);                   // 8 lines polled by 148 x 8 threads: a short pause is enough
                 if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { fail(); break; }
             }
 #pragma unroll
@@ -346,11 +347,15 @@ struct Mega {
         }
         nbar(1, CT);
     }
+    // push_id >= 0: the boundary rows of that vector leave as LL words (push_ll) right AFTER this CTA's reduction words --
+    // the consumers poll the LL words themselves, so the push need not delay the arrival; it overlaps with the reduction's
+    // NVLink latency instead of preceding it
     template <int NV>
-    __device__ void reduce(double (&dot)[NV], int fin, bool tr = false)   // blocking sync point (MPI_Iallreduce + MPI_Wait)
+    __device__ void reduce(double (&dot)[NV], int fin, bool tr = false, int push_id = -1, int region = 0, unsigned epoch = 0u)
     {
         arrive<NV>(dot, false, false);
         if (tr) { mark(11); snap(0); }
+        if (push_id >= 0) push_ll(push_id, region, epoch);
         if (a.comm.world > 1) ++red_epoch;
         finish<NV>(gen, fin, false, tr);
         if (tr) snap(1);
@@ -664,10 +669,9 @@ struct Mega {
             d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
             spmv<EPI_RH_Y>(a.v.p, a.v.s, d4);                               // s = A p, (r#,s)           :88-91
             const unsigned s_epoch = (unsigned)(++halo_epoch);
-            push_ll(V_S, (int)par, s_epoch);
             mark(1);
             d1[0] = d4[0];
-            reduce<1>(d1, FIN_BICG_ALPHA, true);                            // alpha                      :93
+            reduce<1>(d1, FIN_BICG_ALPHA, true, V_S, (int)par, s_epoch);    // alpha (+ boundary rows of s) :93
             mark(2);
             if (stop_now()) break;
             vec<PH_BICG_Q>(d0);                                             // q = r - alpha s            :94
@@ -684,9 +688,8 @@ struct Mega {
             d2[0] = d2[1] = 0.0;
             vec<PH_BICG_XR>(d2);                                            // x, r, (r,r), (r#,r)        :105-114
             const unsigned r_epoch = (unsigned)(++halo_epoch);
-            push_ll(V_R, 2, r_epoch);
             mark(7);
-            reduce<2>(d2, FIN_BICG_BETA);                                   // beta, k++, loop test       :116-120
+            reduce<2>(d2, FIN_BICG_BETA, false, V_R, 2, r_epoch);           // beta, k++, loop test (+ boundary rows of r) :116-120
             mark(8);
             if (stop_now()) break;
             vec<PH_BICG_P>(d0);                                             // p                          :117-119
