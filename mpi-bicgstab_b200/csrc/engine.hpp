@@ -161,7 +161,6 @@ struct bicg_matrix {
     long long ll_stride = 0;
     unsigned long long *peer_ll[bicg::MAX_RANKS] = {};
     long long peer_ll_stride[bicg::MAX_RANKS] = {};
-    int *d_ghost_first = nullptr;
     unsigned long long *d_trace = nullptr;   // BICG_MEGA_TRACE
     // ghost layout
     int ghost_off = 0;           // first ghost column index = roundup(n_loc, 16)

@@ -591,11 +591,11 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     const size_t mail_off = off;  off = align(off + 2 * MAX_RANKS * sizeof(Mailbox));
     const size_t hflag_off = off; off = align(off + MAX_RANKS * sizeof(HaloFlag));
     const size_t msync_off = off; off = align(off + sizeof(MegaSync));
-    // LL halo of the multi-GPU BiCGStab loop (mega.cu: run_bicgstab_multi): three ghost-sized regions of 16-byte
-    // {lo | epoch, hi | epoch} pairs -- s (two parities) and r -- written by the peers, read by the ghost recurrences
+    // LL halo of the persistent kernel's multi-GPU loops (mega.cu): LL_REGIONS ghost-sized regions of 16-byte
+    // {lo | epoch, hi | epoch} pairs, one per pushed vector, written by the peers, polled by the consumers
     const size_t ll_stride = (size_t)round_up(std::max(m->n_ghost, 1), 16);
     const bool want_ll = m->world > 1 && (c.cfg.mega == 2 || c.cfg.mega_lanes > 0 || mega_lanes_for(m->mean_row) == 1);
-    const size_t ll_off = off;    off = align(off + (want_ll ? 3 * ll_stride * 16 : 0));
+    const size_t ll_off = off;    off = align(off + (want_ll ? (size_t)LL_REGIONS * ll_stride * 16 : 0));
     m->arena_bytes = std::max<size_t>(off, (size_t)4 << 20);     // its own allocation granule: the IPC handle maps exactly this
     if (m->world > 1) {
         // exported through CUDA IPC: an allocation of its own (peers map exactly this one), parked and re-used by size
@@ -629,7 +629,6 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     m->comm.timeout_ns = (unsigned long long)c.cfg.peer_timeout_s * 1000000000ull;
     for (int p = 0; p < MAX_RANKS; ++p) { m->comm.mail[p] = m->d_mail; m->comm.hflag[p] = m->d_hflag; m->peer_msync[p] = m->d_msync; }
     std::vector<unsigned char> row_extra;                  // per row: number of peers it is pushed to
-    std::vector<std::vector<PushRunHost>> push_host;       // per push slot
     if (m->world > 1) {
         ArenaHdr mine{};
         mine.handle = m->arena_handle; mine.arena_id = m->arena_id;
@@ -694,7 +693,6 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
             BICG_CUDA(cudaMemcpy(m->d_push_runs[slot], pr.data(), pr.size() * sizeof(PushRun), cudaMemcpyHostToDevice));
             for (const PushRunHost &r : ph)
                 for (int i = r.src; i < r.src + r.len; ++i) if (row_extra[(size_t)i] < 255) ++row_extra[(size_t)i];
-            push_host.push_back(ph);
         }
         m->comm.recv_mask = recv_mask; m->comm.send_mask = send_mask;
     }
@@ -708,29 +706,9 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     // ---- SpMV plan ------------------------------------------------------------------------------------
     choose_spmv_plan(m, h_ptr);
     build_mega_plan(m, h_ptr, row_extra);
-    {
-        // first ghost slot of every owner (slots are grouped by owner, owners ascending: plan.cpp merge_blocks)
-        std::vector<int> gf((size_t)m->world + 1, 0);
-        for (size_t i = 0; i + 3 < m->recv_runs.size(); i += 4) gf[(size_t)m->recv_runs[i + 2] + 1] += m->recv_runs[i + 1];
-        for (int p = 0; p < m->world; ++p) gf[(size_t)p + 1] += gf[(size_t)p];
-        m->d_ghost_first = (int *)c.dev_alloc(gf.size() * sizeof(int));
-        BICG_CUDA(cudaMemcpy(m->d_ghost_first, gf.data(), gf.size() * sizeof(int), cudaMemcpyHostToDevice));
-    }
     if (m->world > 1) {
-        // tell every receiver which of my CTAs push to it (they wait for exactly those flags), and everybody whether
-        // my persistent-kernel plan is usable (the choice of loop implementation must be the same on all ranks)
-        for (int slot = 0; slot < m->npush; ++slot) {
-            unsigned mask[MEGA_MASK_WORDS + 3] = {};
-            if (m->mega.ok)
-                for (const PushRunHost &r : push_host[(size_t)slot])
-                    for (int g = 0; g < m->mega.grid; ++g)
-                        if (m->mega.cta_row[(size_t)g] < r.src + r.len && m->mega.cta_row[(size_t)g + 1] > r.src &&
-                            m->mega.cta_row[(size_t)g + 1] > m->mega.cta_row[(size_t)g])
-                            mask[g >> 5] |= 1u << (g & 31);
-            BICG_CUDA(cudaMemcpyAsync(&m->peer_msync[m->push_peer[slot]]->pusher_mask[m->rank][0], mask, sizeof(mask),
-                                      cudaMemcpyDefault, c.stream));
-            BICG_CUDA(cudaStreamSynchronize(c.stream));          // `mask` is a stack buffer
-        }
+        // everybody must know whether every rank's persistent-kernel plan is usable (the choice of loop implementation, and
+        // with it the synchronisation protocol, must be the same on all ranks): written straight into the peers' arenas
         if (!m->d_ll) m->mega.ok = false;                 // the multi-GPU loops of the persistent kernel need the LL halo regions
         const int ok = m->mega.ok ? 1 : 0;
         for (int p = 0; p < m->world; ++p)
@@ -777,7 +755,6 @@ void matrix_destroy(bicg_matrix *m)
     c.dev_free(m->d_trace);
     c.dev_free(m->mega.d_tile_row); c.dev_free(m->mega.d_tile_nz); c.dev_free(m->mega.d_cta_tile); c.dev_free(m->mega.d_cta_dep);
     c.dev_free(m->mega.d_tile_flag);
-    c.dev_free(m->d_ghost_first);
     if (m->hist_extra) cudaFree(m->hist_extra);
     c.dev_free(m->d_val); c.dev_free(m->d_col); c.dev_free(m->d_ptr);
     if (m->world > 1) c.arena_pool.emplace(m->arena_bytes, Context::ArenaRec{m->arena, m->arena_bytes, m->arena_id, m->arena_handle});

@@ -22,10 +22,14 @@
 //   post / complete : the same, split (MPI_Iallreduce ... SpMV ... MPI_Wait of the pipelined variants);
 //   neighbour wait  : where solver.c has no reduction but the next SpMV gathers what other CTAs just wrote (q, p,
 //              s, ...), a CTA waits only for the CTAs that own the columns its rows reference (a handful for banded
-//              matrices) and -- if its rows reference ghost columns -- for the halo flags of the peers' CTAs that
-//              push them (one flag per pushing CTA, written after that CTA's own system-scope fence).
-// Coherence: gathered vectors are read with plain (L1-cached) loads; every wait ends in an acquire fence at gpu /
-// system scope (SASS: CCTL.IVALL), so lines rewritten by other SMs / peers are re-fetched from L2.
+//              matrices);
+//   halo (N GPUs)   : boundary rows travel to the peers as LL words too (16 bytes per value, push_ll): no system-scope
+//              fence, no flag -- the consumer polls exactly the ghost slots it needs.  In the BiCGStab loop the pushes
+//              ride on the alpha / beta reductions and the ghost copies of q and p are advanced redundantly
+//              (run_bicgstab_multi); the CA / pipelined loops unpack the LL words into the ghost tails (halo_ll, post).
+// Coherence: gathered vectors are read with plain (L1-cached) loads; every neighbour wait ends in an acquire fence at gpu
+// scope (SASS: MEMBAR + CCTL.IVALL), so rows rewritten by other SMs are re-fetched from L2; values from peers are taken
+// from the LL words with system-scope loads and re-stored locally by the consuming CTA.
 // Every wait is bounded by CommDev::timeout_ns (BICG_PEER_TIMEOUT_S): a lost CTA or rank raises Scalars::error instead of hanging the GPU.
 #include "mega.cuh"
 #include "vec_body.cuh"
@@ -125,10 +129,9 @@ struct Mega {
     unsigned posted_gen;          // generation of the reduction posted and not yet completed
     unsigned long long halo_epoch;
     int dep_lo, dep_hi;           // CTAs owning the own columns this CTA's rows reference
-    unsigned need_senders;        // ranks whose halo pushes this CTA's rows reference
     unsigned push_slots;          // push slots (peers) that need rows of this CTA
+    int ghost_lo, ghost_hi;       // ghost slots this CTA's rows gather [lo, hi)
     int gs_lo, gs_hi;             // ghost slots this CTA keeps up to date itself (multi-GPU bicgstab: redundant recurrences)
-    unsigned gs_senders;          // ranks that fill those slots
     bool reads_ghost;             // this CTA's rows gather ghost columns
     bool is_reducer;              // N > 1: the CTA that adds up this GPU's slots and posts them to the peers' mailboxes
     size_t stage_bytes;
@@ -150,23 +153,19 @@ struct Mega {
     }
 
     // ---------------------------------------------------------------- arrive ------------------------------
-    // Publish NV partial sums (NV = 0: presence only) for generation ++gen.  halo: this synchronisation point also
-    // carries a halo exchange -- CTAs that pushed rows to peers fence at system scope and raise their flag there.
-    // release: the arrival also PUBLISHES this CTA's stores of the phase (rows that other CTAs / peers gather after
-    // waiting for it): CTA barrier + release fence before the words go out.  A pure reduction arrival does not need it:
-    // the reduced values travel inside the words, nobody gathers this CTA's rows before its next releasing arrival (a
-    // neighbour wait always precedes a gather), and its own earlier gathers completed before the dots that depend on them.
+    // Publish NV partial sums (NV = 0: presence only) for generation ++gen.
+    // release: the arrival also PUBLISHES this CTA's stores of the phase (rows that other CTAs gather after waiting for
+    // it): CTA barrier + release fence before the words go out.  A pure reduction arrival does not need it: the reduced
+    // values travel inside the words, nobody gathers this CTA's rows before its next releasing arrival (a neighbour wait
+    // always precedes a gather), and its own earlier gathers completed before the dots that depend on them.
     template <int NV>
-    __device__ void arrive(double (&dot)[NV > 0 ? NV : 1], bool halo, bool release = true)
+    __device__ void arrive(double (&dot)[NV > 0 ? NV : 1], bool release)
     {
         // a CTA barrier (inside cblock_sum, or the explicit one) puts every consumer's stores of the phase before the fence
         if (NV > 0) cblock_sum<(NV > 0 ? NV : 1), CT>(dot, sh.scratch);
         else nbar(1, CT);
         ++gen;
-        if (halo) ++halo_epoch;
-        const bool pushed = halo && push_slots != 0u;
         if (tid < 32) {
-            // release: the CTA barrier above + this fence order every store of the CTA before the words below
             if (release) fence_gpu();
             MegaSlot *s = &a.sync->slot[gen & (MEGA_RING - 1)][blockIdx.x];
             constexpr int NW = NV > 0 ? 2 * NV : 1;
@@ -181,19 +180,12 @@ struct Mega {
                 }
                 st_ll_gpu(&s->w[lane], ll_pack(data, gen));
             }
-            if (pushed) {
-                // rows that went to peers: order the NVLink stores at system scope, THEN raise this CTA's flag over there.
-                // After the slot words, so that the (latency-bound) reduction / the local neighbours do not wait for it.
-                fence_sys();
-#pragma unroll
-                for (int s2 = 0; s2 < MAX_RANKS - 1; ++s2)
-                    if (lane == s2 && ((push_slots >> s2) & 1u)) st_flag_sys(a.push.hflag_dst[s2] + blockIdx.x, halo_epoch);
-            }
         }
     }
 
     // ---------------------------------------------------------------- neighbour wait ----------------------
-    __device__ void wait_nbr(bool halo)
+    // wait for the CTAs (of this GPU) that own the columns this CTA's rows gather
+    __device__ void wait_nbr()
     {
         if (tid < 32) {
             bool ok = true;
@@ -207,33 +199,17 @@ struct Mega {
                     if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
                 }
             }
-            const bool remote = halo && need_senders != 0u;
-            if (remote) {
-                for (int s = 0; s < a.comm.world; ++s) {
-                    if (!((need_senders >> s) & 1u)) continue;
-                    const unsigned long long *f = a.sync->hflag[s];
-                    for (int i = lane; i < MEGA_MAX_CTAS; i += 32) {
-                        if (!((a.sync->pusher_mask[s][i >> 5] >> (i & 31)) & 1u)) continue;
-                        unsigned spins = 0;
-                        while (ld_relaxed_sys(&f[i]) < halo_epoch) {
-                            poll_pause(++spins);
-                            if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
-                        }
-                    }
-                }
-            }
-            if (remote) fence_sys(); else fence_gpu();       // acquire (+ L1 invalidate): the gathers that follow see the data
+            fence_gpu();                                     // acquire (+ L1 invalidate): the gathers that follow see the data
             if (!__all_sync(0xffffffffu, ok) && lane == 0) fail();
         }
         nbar(1, CT);
         if (sh.flags[3]) { if (tid == 0) { sh.sc.error = 1; sh.sc.done = 1; } nbar(1, CT); }
     }
-    __device__ void sync_nbr(bool halo)
+    __device__ void sync_nbr()
     {
         double d0[1] = {0.0};
-        halo = halo && a.comm.world > 1;
-        arrive<0>(d0, halo);
-        wait_nbr(halo);
+        arrive<0>(d0, true);
+        wait_nbr();
     }
 
     // ---------------------------------------------------------------- reductions --------------------------
@@ -353,24 +329,28 @@ struct Mega {
     template <int NV>
     __device__ void reduce(double (&dot)[NV], int fin, bool tr = false, int push_id = -1, int region = 0, unsigned epoch = 0u)
     {
-        arrive<NV>(dot, false, false);
+        arrive<NV>(dot, false);
         if (tr) { mark(11); snap(0); }
         if (push_id >= 0) push_ll(push_id, region, epoch);
         if (a.comm.world > 1) ++red_epoch;
         finish<NV>(gen, fin, false, tr);
         if (tr) snap(1);
     }
+    // MPI_Iallreduce + the halo of vector `id` that the SpMV hiding the reduction gathers (LL region `region`)
     template <int NV>
-    __device__ void post(double (&dot)[NV], bool halo)          // MPI_Iallreduce (+ the halo of the SpMV that hides it)
+    __device__ void post(double (&dot)[NV], int id, int region)
     {
-        halo = halo && a.comm.world > 1;
-        arrive<NV>(dot, halo);
+        const bool multi = a.comm.world > 1;
+        const unsigned ep = multi ? (unsigned)(++halo_epoch) : 0u;
+        arrive<NV>(dot, true);
         posted_gen = gen;
-        if (a.comm.world > 1) {
+        if (multi) {
             ++red_epoch;
             if (is_reducer) { local_reduce<NV>(gen); if (tid < 32) post_mail<NV>(); }
+            push_ll(id, region, ep);
         }
-        wait_nbr(halo);
+        wait_nbr();
+        if (multi) unpack_ll(id, region, ep);
     }
     // MPI_Wait.  after_spmv: the SpMV that hid the reduction gathered a vector that the NEXT phase overwrites in place
     // (pipelined loops: y = w - alpha z is stored over w right after t = A w): the reduction was published BEFORE that
@@ -381,7 +361,7 @@ struct Mega {
     {
         if (after_spmv) {
             double d0[1] = {0.0};
-            arrive<0>(d0, false, false);
+            arrive<0>(d0, false);
             if (tid < RED_THREADS && tid < (int)gridDim.x && tid != (int)blockIdx.x) {
                 const unsigned long long *w = a.sync->slot[gen & (MEGA_RING - 1)][tid].w;
                 const unsigned long long t0 = globaltimer_ns();
@@ -508,57 +488,13 @@ struct Mega {
         for (; i < hi2; i += 2 * CT) body<PH, Pairs<1, 2 * CT>>(a.v, i, c, dot);
         if (tid == 0 && hi2 < row_hi) body<PH, Contig<1>>(a.v, hi2, c, dot);
     }
-    // copy the rows of vector `id` that peers gather into their ghost regions (NVLink stores); the flag follows in arrive()
-    __device__ void push(int id, int dst_id = -1)
-    {
-        if (a.comm.world == 1 || push_slots == 0u) return;
-        if (dst_id < 0) dst_id = id;
-        nbar(1, CT);                                  // the rows being pushed are final
-        PushDesc pd;
-        pd.npeers = a.push.npeers; pd.fence_writers = 0;
-        pd.src = a.vec_base + (long long)id * a.vstride;
-#pragma unroll
-        for (int s = 0; s < MAX_RANKS - 1; ++s) {
-            pd.dst[s] = a.push.ghost0[s] + (long long)dst_id * a.push.vstride[s];
-            pd.runs[s] = a.push.runs[s];
-            pd.nruns[s] = ((push_slots >> s) & 1u) ? a.push.nruns[s] : 0;
-        }
-        push_chunk(pd, row_lo, row_hi, tid, CT);
-    }
-
     // ---------------------------------------------------------------- multi-GPU helpers ---------------------
-    // wait for the halo flags (epoch halo_epoch) of the peers' CTAs that fill the ghost slots in `senders`
-    __device__ void halo_wait(unsigned senders)
-    {
-        if (tid < 32) {
-            bool ok = true;
-            if (senders != 0u) {
-                const unsigned long long t0 = globaltimer_ns();
-                for (int s = 0; s < a.comm.world; ++s) {
-                    if (!((senders >> s) & 1u)) continue;
-                    const unsigned long long *f = a.sync->hflag[s];
-                    for (int i = lane; i < MEGA_MAX_CTAS; i += 32) {
-                        if (!((a.sync->pusher_mask[s][i >> 5] >> (i & 31)) & 1u)) continue;
-                        unsigned spins = 0;
-                        while (ld_relaxed_sys(&f[i]) < halo_epoch) {
-                            poll_pause(++spins);
-                            if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
-                        }
-                    }
-                }
-                fence_sys();
-            }
-            if (!__all_sync(0xffffffffu, ok) && lane == 0) fail();
-        }
-        nbar(1, CT);
-        if (sh.flags[3]) { if (tid == 0) { sh.sc.error = 1; sh.sc.done = 1; } nbar(1, CT); }
-    }
     // releasing arrival + wait for EVERY CTA of this GPU (all == true) or for the CTAs owning the gathered columns
     __device__ void sync_local(bool all)
     {
         double d0[1] = {0.0};
-        arrive<0>(d0, false, true);
-        if (!all) { wait_nbr(false); return; }
+        arrive<0>(d0, true);
+        if (!all) { wait_nbr(); return; }
         if (tid < RED_THREADS) {
             if (tid < (int)gridDim.x && tid != (int)blockIdx.x) {
                 const unsigned long long *w = a.sync->slot[gen & (MEGA_RING - 1)][tid].w;
@@ -574,15 +510,6 @@ struct Mega {
         }
         nbar(1, CT);
         if (sh.flags[3]) { if (tid == 0) { sh.sc.error = 1; sh.sc.done = 1; } nbar(1, CT); }
-    }
-    // reduction whose arrival also carries a halo exchange: the pushers' flags go out right after the reduction words
-    template <int NV>
-    __device__ void reduce_halo(double (&dot)[NV], int fin, bool tr = false)
-    {
-        arrive<NV>(dot, true, false);
-        if (tr) mark(11);
-        ++red_epoch;
-        finish<NV>(gen, fin, false, tr);
     }
     // Boundary rows of vector `id` -> LL region `region` of the peers that gather them: every element travels as one
     // 16-byte pair of self-validating words {lo | epoch, hi | epoch} (dev.cuh), so the receiver needs neither a flag nor
@@ -624,6 +551,30 @@ struct Mega {
         }
         return ll_decode(w0, w1);
     }
+    // LL region -> plain ghost tail of vector `id`, for exactly the ghost slots this CTA's rows gather (several CTAs may
+    // unpack the same slot: the copy is out of place and writes the same bits).  Ends with a CTA barrier.
+    __device__ void unpack_ll(int id, int region, unsigned epoch)
+    {
+        if (ghost_hi > ghost_lo) {
+            double *g = a.vec_base + (long long)id * a.vstride + a.ghost_off;
+            const unsigned long long *ll = a.ll + 2ll * region * a.ll_stride;
+            const unsigned long long t0 = globaltimer_ns();
+            for (int i = ghost_lo + tid; i < ghost_hi; i += CT) g[i] = ll_take(ll + 2ll * i, epoch, t0);
+        }
+        nbar(1, CT);
+    }
+    // halo exchange of the CA / pipelined loops where solver.c has no reduction: boundary rows leave as LL words, the CTA waits
+    // for the CTAs owning the gathered columns, then unpacks the ghost slots it gathers
+    __device__ void halo_ll(int id, int region)
+    {
+        if (a.comm.world == 1) { sync_nbr(); return; }
+        const unsigned ep = (unsigned)(++halo_epoch);
+        double d0[1] = {0.0};
+        arrive<0>(d0, true);
+        push_ll(id, region, ep);
+        wait_nbr();
+        unpack_ll(id, region, ep);
+    }
     // this CTA's share of the ghost slots, element-wise exactly like the owner's rows (same operands, same operation
     // order -> bitwise the values the owner computes)
     __device__ void ghost_q(int sregion, unsigned s_epoch)                 // q = r - alpha s            solver.c:94
@@ -638,7 +589,7 @@ struct Mega {
     {
         const double be = sh.sc.beta, nbo = -sh.sc.beta * sh.sc.omega;
         double *p = a.v.p + a.ghost_off, *r = a.v.r + a.ghost_off;
-        const unsigned long long *sll = a.ll + 2ll * sregion * a.ll_stride, *rll = a.ll + 2ll * 2 * a.ll_stride;
+        const unsigned long long *sll = a.ll + 2ll * sregion * a.ll_stride, *rll = a.ll + 2ll * LL_R * a.ll_stride;
         const unsigned long long t0 = globaltimer_ns();
         for (int i = gs_lo + tid; i < gs_hi; i += CT) {
             const double rn = ll_take(rll + 2ll * i, r_epoch, t0);      // the owner's new r (pushed with the beta reduction)
@@ -671,11 +622,11 @@ struct Mega {
             const unsigned s_epoch = (unsigned)(++halo_epoch);
             mark(1);
             d1[0] = d4[0];
-            reduce<1>(d1, FIN_BICG_ALPHA, true, V_S, (int)par, s_epoch);    // alpha (+ boundary rows of s) :93
+            reduce<1>(d1, FIN_BICG_ALPHA, true, V_S, LL_S0 + (int)par, s_epoch);    // alpha (+ boundary rows of s) :93
             mark(2);
             if (stop_now()) break;
             vec<PH_BICG_Q>(d0);                                             // q = r - alpha s            :94
-            ghost_q((int)par, s_epoch);
+            ghost_q(LL_S0 + (int)par, s_epoch);
             mark(3);
             sync_local(reads_ghost);
             mark(4);
@@ -689,11 +640,11 @@ struct Mega {
             vec<PH_BICG_XR>(d2);                                            // x, r, (r,r), (r#,r)        :105-114
             const unsigned r_epoch = (unsigned)(++halo_epoch);
             mark(7);
-            reduce<2>(d2, FIN_BICG_BETA, false, V_R, 2, r_epoch);           // beta, k++, loop test (+ boundary rows of r) :116-120
+            reduce<2>(d2, FIN_BICG_BETA, false, V_R, LL_R, r_epoch);          // beta, k++, loop test (+ boundary rows of r) :116-120
             mark(8);
             if (stop_now()) break;
             vec<PH_BICG_P>(d0);                                             // p                          :117-119
-            ghost_p((int)par, s_epoch, r_epoch);
+            ghost_p(LL_S0 + (int)par, s_epoch, r_epoch);
             mark(9);
             sync_local(reads_ghost);
             mark(10);
@@ -716,9 +667,8 @@ struct Mega {
             mark(2);
             if (stop_now()) break;
             vec<PH_BICG_Q>(d0);                                             // q = r - alpha s            :94
-            push(V_R);
             mark(3);
-            sync_nbr(true);
+            sync_nbr();
             mark(4);
             d4[0] = d4[1] = 0.0;
             spmv<EPI_QY_YY>(a.v.r, a.v.y, d4);                              // y = A q, (q,y), (y,y)      :96-102
@@ -733,9 +683,8 @@ struct Mega {
             mark(8);
             if (stop_now()) break;
             vec<PH_BICG_P>(d0);                                             // p                          :117-119
-            push(V_P);
             mark(9);
-            sync_nbr(true);
+            sync_nbr();
             mark(10);
             ++trace_it;
         }
@@ -747,8 +696,7 @@ struct Mega {
         d0[0] = 0.0;
         while (true) {
             vec<PH_CA_PS>(d0);                                              // p, s                       :217-222
-            push(V_S);
-            sync_nbr(true);
+            halo_ll(V_S, LL_S0);
             d4[0] = 0.0;
             spmv<EPI_NONE>(a.v.s, a.v.z, d4);                               // z = A s                    :224
             nbar(1, CT);                                                    // own rows of z written by other warps
@@ -758,8 +706,7 @@ struct Mega {
             if (stop_now()) break;
             d1[0] = 0.0;
             vec<PH_CA_XR>(d1);                                              // x, r, local (r,r)          :233-236
-            push(V_R);
-            sync_nbr(true);
+            halo_ll(V_R, LL_R);
             d4[0] = d4[1] = d4[2] = d4[3] = 0.0;
             spmv<EPI_CA4>(a.v.r, a.v.w, d4);                                // w = A r, 4 dots            :238-247
             d5[0] = d4[0]; d5[1] = d4[1]; d5[2] = d4[2]; d5[3] = d4[3]; d5[4] = d1[0];
@@ -780,17 +727,14 @@ struct Mega {
                 vec<PH_PIPE_1>(d2);                                         // p,s,z,q,y + (q,y),(y,y)    :352-364
             } else {
                 vec<PH_RR_P>(d0);                                           // p                          :494-496
-                push(V_P);
-                sync_nbr(true);
+                halo_ll(V_P, LL_P);
                 spmv<EPI_NONE>(a.v.p, a.v.s, d4);                           // s = A p                    :499
-                push(V_S);
-                sync_nbr(true);
+                halo_ll(V_S, LL_S0);
                 spmv<EPI_NONE>(a.v.s, a.v.z, d4);                           // z = A s                    :500
                 nbar(1, CT);
                 vec<PH_QY>(d2);                                             // q, y, (q,y), (y,y)         :509-512
             }
-            push(V_Z);
-            post<2>(d2, true);                                              // MPI_Iallreduce x2
+            post<2>(d2, V_Z, LL_Z);                                         // MPI_Iallreduce x2 (+ halo of z)
             spmv<EPI_NONE>(a.v.z, a.v.v, d4);                               // v = A z hides it           :365 / 513
             complete<2>(FIN_OMEGA2, false);                                 // MPI_Wait x2 -> omega       :366-369
             if (stop_now()) break;
@@ -799,19 +743,16 @@ struct Mega {
                 vec<PH_PIPE_3>(d5);                                         // x, r, w + 5 dots           :370-380
             } else {
                 vec<PH_RR_X>(d0);                                           // x                          :518-519
-                push(V_X);
-                sync_nbr(true);
+                halo_ll(V_X, LL_X);
                 spmv<EPI_NONE>(a.v.x, a.v.ax, d4);                          // Ax = A x                   :523
                 nbar(1, CT);
                 vec<PH_RR_R>(d0);                                           // r = b - Ax                 :524-525
-                push(V_R);
-                sync_nbr(true);
+                halo_ll(V_R, LL_R);
                 spmv<EPI_NONE>(a.v.r, a.v.w, d4);                           // w = A r                    :526
                 nbar(1, CT);
                 vec<PH_RR_DOTS>(d5);                                        // 5 dots                     :533-539
             }
-            push(V_W);
-            post<5>(d5, true);                                              // MPI_Iallreduce x5
+            post<5>(d5, V_W, LL_W);                                         // MPI_Iallreduce x5 (+ halo of w)
             spmv<EPI_NONE>(a.v.w, a.v.t, d4);                               // t = A w hides it           :381 / 540
             complete<5>(FIN_CAPIPE_END, true);                              // MPI_Wait x5 -> beta, alpha :382-388
             if (stop_now()) break;
@@ -909,24 +850,18 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
         };
         m.dep_lo = 1; m.dep_hi = 0;
         if (dep.x <= dep.y) { m.dep_lo = max(0, cta_of_row(dep.x)); m.dep_hi = min(G - 1, cta_of_row(dep.y)); }
-        m.need_senders = 0u;
-        if (a.comm.world > 1 && dep.z <= dep.w)
-            for (int p = 0; p < a.comm.world; ++p)
-                if (a.ghost_first[p] <= dep.w && a.ghost_first[p + 1] > dep.z) m.need_senders |= 1u << p;
         m.reads_ghost = a.comm.world > 1 && dep.z <= dep.w;
+        m.ghost_lo = m.reads_ghost ? dep.z : 0; m.ghost_hi = m.reads_ghost ? dep.w + 1 : 0;
         // the reducer sits in the middle of the row range: on banded matrices the CTAs at the ends are busy pushing boundary
         // rows over NVLink (slow per SM) right before the reductions, and everybody would wait for them twice
         m.is_reducer = (int)blockIdx.x == G / 2;
-        m.gs_lo = m.gs_hi = 0; m.gs_senders = 0u;
+        m.gs_lo = m.gs_hi = 0;
         if (a.comm.world > 1) {
             // ghost slots are shared out evenly (16-slot granules) over the CTAs
-            const int ng = a.ghost_first[a.comm.world];
+            const int ng = a.n_ghost;
             const int chunk = ((ng + G - 1) / G + 15) & ~15;
             m.gs_lo = min(ng, (int)blockIdx.x * chunk);
             m.gs_hi = min(ng, m.gs_lo + chunk);
-            if (m.gs_hi > m.gs_lo)
-                for (int p = 0; p < a.comm.world; ++p)
-                    if (a.ghost_first[p] < m.gs_hi && a.ghost_first[p + 1] > m.gs_lo) m.gs_senders |= 1u << p;
         }
         m.push_slots = 0u;
         if (a.comm.world > 1) {
@@ -938,7 +873,7 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
             }
         }
         nbar(1, CT);
-        if (a.comm.world > 1 && (m.need_senders != 0u || m.gs_senders != 0u)) {
+        if (a.comm.world > 1 && (m.reads_ghost || m.gs_hi > m.gs_lo)) {
             // the vectors the first phases read were pushed by the init kernels (kernel-per-phase protocol)
             if (tid < 32 && !halo_wait(a.comm, sh.sc.halo_epoch) && tid == 0) { sh.sc.error = 1; sh.sc.done = 1; }
             if (tid < 32) fence_sys();

@@ -8,7 +8,6 @@ namespace bicg {
 constexpr int MEGA_MAX_CTAS   = 160;   // >= SM count (148 on B200); one CTA per SM
 constexpr int MEGA_RING       = 8;     // generations of arrival slots kept (a CTA is never more than 3 ahead of another)
 constexpr int MEGA_SLOT_WORDS = 16;    // 8 doubles as LL words
-constexpr int MEGA_MASK_WORDS = MEGA_MAX_CTAS / 32;
 
 // What a CTA leaves at a synchronisation point: its partial dot products as self-validating LL words
 // {generation | 32 data bits} (dev.cuh).  One 128-byte line per CTA and generation, written once, polled by the CTAs
@@ -23,27 +22,25 @@ struct alignas(128) MegaState {
     int plan_ok[MAX_RANKS];             // written by rank p at plan time: its persistent-kernel plan is usable
 };
 
-// Lives in the IPC-shared arena: `mail`, `hflag`, `pusher_mask` and `st.plan_ok` are written by the peers.
+// Lives in the IPC-shared arena: `mail` and `st.plan_ok` are written by the peers.
 struct MegaSync {
     MegaState st;
     MegaSlot  slot[MEGA_RING][MEGA_MAX_CTAS];
     MegaSlot  mail[2][MAX_RANKS];                           // [epoch parity][source rank]: that rank's local sums
-    unsigned long long hflag[MAX_RANKS][MEGA_MAX_CTAS];     // [sender][sender's CTA] = halo epoch that CTA has pushed
-    unsigned pusher_mask[MAX_RANKS][MEGA_MASK_WORDS + 3];   // [sender]: which of its CTAs push to this rank
 };
 
-// where the boundary runs of any arena vector go on the peers (the per-vector PushDesc is derived on the device)
+// where the boundary runs of the arena vectors go on the peers (LL halo regions, see LLRegion)
 struct PushPlan {
     int npeers;
-    int peer[MAX_RANKS - 1];                 // rank of push slot i
-    double *ghost0[MAX_RANKS - 1];           // peer-mapped address of vector 0's ghost region on that rank
-    long long vstride[MAX_RANKS - 1];        // that rank's distance between consecutive vectors (doubles)
+    int peer[MAX_RANKS - 1];                        // rank of push slot i
     const PushRun *runs[MAX_RANKS - 1];
     int nruns[MAX_RANKS - 1];
-    unsigned long long *hflag_dst[MAX_RANKS - 1];   // that rank's sync->hflag[this rank]: one flag per pushing CTA
     unsigned long long *ll_dst[MAX_RANKS - 1];      // that rank's LL halo regions (region k at + k * 2 * ll_stride words)
     long long ll_stride[MAX_RANKS - 1];             // ... its region length in elements
 };
+
+// LL halo regions (one per pushed vector; s has two because the multi-GPU BiCGStab loop double-buffers it)
+enum LLRegion : int { LL_S0 = 0, LL_S1, LL_R, LL_P, LL_Z, LL_X, LL_W, LL_REGIONS };
 
 constexpr int MEGA_TRACE_ITERS = 256, MEGA_TRACE_SLOTS = 16;
 
@@ -53,7 +50,7 @@ struct MegaArgs {
     CommDev  comm;              // kernel-per-phase protocol state (only for the halo wait on entry)
     MegaSync *sync;             // this rank's
     MegaSlot *peer_mail[MAX_RANKS];              // rank p's sync->mail[0]
-    const int *ghost_first;     // [world + 1]: first ghost slot received from each owner (slots are grouped by owner)
+    int n_ghost;                // ghost slots of this rank
     const int4 *cta_dep;        // [grid]: min / max own column, min / max ghost slot referenced by the CTA's rows
     const double   *val;
     const unsigned *col;
@@ -68,7 +65,7 @@ struct MegaArgs {
     double *vec_base; long long vstride;   // arena vectors: vec(id) = vec_base + id * vstride
     VecPtrs v;
     PushPlan push;
-    const unsigned long long *ll;          // this rank's LL halo regions, [3][ll_stride] pairs: s (parity 0, 1), r
+    const unsigned long long *ll;          // this rank's LL halo regions, [LL_REGIONS][ll_stride] pairs
     long long ll_stride;
     int method;                 // 0 bicgstab, 1 ca_bicgstab, 2 pipe_bicgstab, 3 pipe_bicgstab_rr
     int krr, nrr;

@@ -87,7 +87,7 @@ struct Seq {
         MegaArgs a{};
         a.sc = m->d_sc; a.hist = m->d_hist; a.comm = m->comm; a.sync = m->d_msync;
         for (int p = 0; p < MAX_RANKS; ++p) a.peer_mail[p] = &m->peer_msync[p]->mail[0][0];
-        a.ghost_first = m->d_ghost_first; a.cta_dep = m->mega.d_cta_dep;
+        a.n_ghost = m->n_ghost; a.cta_dep = m->mega.d_cta_dep;
         a.val = m->d_val; a.col = m->d_col; a.ptr = m->d_ptr;
         a.tile_row = m->mega.d_tile_row; a.tile_nz = m->mega.d_tile_nz; a.cta_tile = m->mega.d_cta_tile;
         a.tile_flag = m->mega.d_tile_flag;
@@ -99,11 +99,8 @@ struct Seq {
         for (int s = 0; s < a.push.npeers; ++s) {
             const int d = m->push_peer[s];
             a.push.peer[s] = d;
-            a.push.ghost0[s] = (double *)((char *)m->peer_base[d] + m->peer_vec_off[d]) + m->peer_ghost_off[d];
-            a.push.vstride[s] = m->peer_vstride[d];
             a.push.runs[s] = m->d_push_runs[s];
             a.push.nruns[s] = m->push_nruns[s];
-            a.push.hflag_dst[s] = &m->peer_msync[d]->hflag[m->rank][0];
             a.push.ll_dst[s] = m->peer_ll[d];
             a.push.ll_stride[s] = m->peer_ll_stride[d];
         }
