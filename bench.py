@@ -358,7 +358,13 @@ def run_b200(args, w):
     B.set_options(device=local, quiet=1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        B.comm_init_torch()
+        # the library's own bootstrap transport, as the reference's main.c gets it from MPI_Init of include/compat/mpi.h:
+        # POSIX shared memory (csrc/shm_boot.cpp; reads torchrun's RANK / WORLD_SIZE / MASTER_PORT).  BENCH_BOOT=torch routes
+        # the bootstrap bytes through torch.distributed instead.  torch itself is only used for this script's barriers.
+        if os.environ.get("BENCH_BOOT", "shm") == "torch":
+            B.comm_init_torch()
+        elif B.lib.bicg_shm_bootstrap() != 0:
+            raise RuntimeError("bicg_shm_bootstrap failed")
     method = w["method"]
     n_glob_g = w["g"] * world if w["kind"] == "random" else w["g"]
 
@@ -465,7 +471,10 @@ def run_b200(args, w):
     B.set_options(cache=1)
     dm.destroy()
     if world > 1:                      # collective teardown first: rank 0 then spends up to a minute in the CPU legs alone
-        B.comm_finalize()
+        if os.environ.get("BENCH_BOOT", "shm") == "torch":
+            B.comm_finalize()
+        else:
+            B.lib.bicg_shm_shutdown()
         dist.destroy_process_group()
 
     if rank == 0:

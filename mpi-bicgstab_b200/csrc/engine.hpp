@@ -44,7 +44,7 @@ struct Config {
     int mega_lanes = 0;          // lanes per row of the persistent kernel's SpMV (0 choose from the mean row length)
     int l2_hint = 1;             // matrix stream loaded with an L2 evict-first policy (persistent kernel)
     int row_weight = 1200;       // per-row cost (byte equivalents) next to 24 B per entry when CTA row ranges are balanced
-    int boundary_weight = 600;   // extra work (bytes) charged per pushed row when CTA row ranges are balanced
+    int boundary_weight = 300;   // extra work (bytes) charged per pushed row when CTA row ranges are balanced
     int device = -1;
     int halo_gap = 64;
     int verbose = 0;
