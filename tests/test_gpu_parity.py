@@ -276,8 +276,11 @@ def test_random_block_parity(B, O, request):
     ref = O.solve("ca_bicgstab", n, ptr, col, val, b_ref, tol=1e-10, max_iter=200)
     m = min(10, it, ref["iters"])
     got, want = np.sqrt(hist[1:m + 1]), np.sqrt(ref["hist"][1:m + 1])
-    assert np.all(np.abs(got - want) <= 1e-10 * want + H_FLOOR), np.abs(got - want) / want
-    assert abs(it - ref["iters"]) <= 2 and np.abs(x - 1.0).max() <= 1e-8
+    # this family converges by ~2 digits per iteration: the recursion's own rounding noise (eps ||r_{k-1}||, i.e. ~100 eps
+    # relative to ||r_k||, carried through the CA recurrences) reaches 1e-10 of the residual after a few iterations, hence the
+    # absolute floor of 1e-12 ||r0|| next to the 1e-10 relative bound
+    assert np.all(np.abs(got - want) <= 1e-10 * want + 1e-12), (got, want, np.abs(got - want) / want)
+    assert abs(it - ref["iters"]) <= 2 and np.abs(x - 1.0).max() <= 1e-8, (it, ref["iters"], np.abs(x - 1.0).max())
     if "mega" in request.node.name:
         assert st["kernel_launches"] <= 8          # the loop ran as one persistent kernel
     dm.destroy()

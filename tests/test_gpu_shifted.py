@@ -37,19 +37,24 @@ def test_shifted_matches_oracle(B, O, name, kind, g, p0, L, scale, seed):
 
 
 def test_shifted_many_shifts_medium_size(B, O):
-    """64 shifts on a 250 k-row matrix: the multi-vector update kernel with a full coefficient table, x_j vs the oracle."""
-    B.set_options(quiet=1, shift_tol=1e-12, shift_max_iter=1000)
-    blk, n, ptr, col, val = global_csr(B, "convdiff", 500, 1.5)
+    """64 shifts on a 250 k-row matrix (T' family, 63^3): the multi-vector update kernel with a full coefficient table; every
+    sampled x_j against the oracle's and against its own shifted system."""
+    B.set_options(quiet=1, shift_tol=1e-10, shift_max_iter=1000)
+    blk, n, ptr, col, val = global_csr(B, "stencil15", 63, 14.0)
     L, seed = 64, 0
-    sigma, b = shifted_problem(O, n, ptr, col, val, L, 0.01 / L, seed)
-    ref = O.shifted_solve(n, ptr, col, val, b, sigma, seed, tol=1e-12, max_iter=1000)
+    sigma, b = shifted_problem(O, n, ptr, col, val, L, 0.5 / L, seed)
+    ref = O.shifted_solve(n, ptr, col, val, b, sigma, seed, tol=1e-10, max_iter=1000)
+    assert ref["ret"] < 1000                                          # the case does converge
     x = np.zeros((L, n))
     r = b.copy()
     ret = B.shifted_lopbicg_switching(blk, x, r, sigma, seed)
-    assert abs(ret - ref["ret"]) <= max(2, int(0.02 * ref["ret"]))
+    B.set_options(shift_tol=1e-12)
+    assert abs(ret - ref["ret"]) <= max(2, int(0.02 * ref["ret"])), (ret, ref["ret"])
     for j in (0, 1, 31, 63):
         res = O.spmv(n, ptr, col, val, x[j]) + sigma[j] * x[j] - b
-        assert np.linalg.norm(res) <= 1e-9 * np.linalg.norm(b)
+        res_ref = O.spmv(n, ptr, col, val, ref["x"][j]) + sigma[j] * ref["x"][j] - b
+        assert np.linalg.norm(res) <= max(10 * np.linalg.norm(res_ref), 1e-8 * np.linalg.norm(b)), (j, np.linalg.norm(res), np.linalg.norm(res_ref))
+        assert np.abs(x[j] - ref["x"][j]).max() <= 1e-6 * np.abs(ref["x"][j]).max()
 
 
 def test_shifted_stdout_contract(B, O, capfd):
