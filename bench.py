@@ -496,7 +496,7 @@ def run_b200(args, w):
             ach = per_rank * iters / (loop_ms * 1e-3) / 1e9
             tpi = read_traffic("mega_dram_bytes_per_iteration")
             roofline = {"bound": "hbm", "kernel": f"bicg_mega_kernel (persistent solver loop of {method}: 2 SpMV phases + the fused "
-                                                  "vector phases + 4-5 grid barriers per iteration)",
+                                                  "vector phases + 3 reductions and 2 neighbour waits per iteration; one launch per solve)",
                         "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": ach / peak, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": per_rank * iters / args.steps,
@@ -529,7 +529,8 @@ def run_b200(args, w):
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
-        line["roofline"]["traffic_source"] = "profiles/spmv_traffic.json (ncu dram__bytes of the same kernel on the same matrix), not measured in this run"
+        line["roofline"]["traffic_source"] = ("profiles/spmv_traffic.json (ncu --set full dram__bytes_read + dram__bytes_write of the same kernel on the "
+                                              "same matrix, profiles/r02c_mega_kernel_ncu_full.json), not measured in this run")
         rr = None
         if not args.no_cpu:
             try:

@@ -42,6 +42,7 @@ struct Config {
     int mega_threads = 0;        // 0 choose (512, else 256)
     int mega_trace = 0;
     int mega_lanes = 0;          // lanes per row of the persistent kernel's SpMV (0 choose from the mean row length)
+    int gather_cg = -1;          // SpMV gathers of the persistent kernel through L2 only + fence-free neighbour waits (-1: default = off)
     int l2_hint = 1;             // matrix stream loaded with an L2 evict-first policy (persistent kernel)
     int row_weight = 1200;       // per-row cost (byte equivalents) next to 24 B per entry when CTA row ranges are balanced
     int boundary_weight = 300;   // extra work (bytes) charged per pushed row when CTA row ranges are balanced

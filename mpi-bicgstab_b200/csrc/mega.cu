@@ -199,7 +199,7 @@ struct Mega {
                     if ((spins & 255u) == 0u && globaltimer_ns() - t0 > a.comm.timeout_ns) { ok = false; break; }
                 }
             }
-            fence_gpu();                                     // acquire (+ L1 invalidate): the gathers that follow see the data
+            if (!a.gather_cg) fence_gpu();                   // acquire (+ L1 invalidate): the gathers that follow see the data
             if (!__all_sync(0xffffffffu, ok) && lane == 0) fail();
         }
         nbar(1, CT);
@@ -376,8 +376,15 @@ struct Mega {
     }
 
     // ---------------------------------------------------------------- SpMV over this CTA's tiles ----------
+    // gather_cg (BICG_GATHER_CG=1, multi-GPU experiments): x is gathered with L2-only loads; the neighbour waits then need no
+    // acquire fence (no L1 line can be stale), which takes a MEMBAR + CCTL.IVALL off every neighbour wait
     template <int EPI>
     __device__ void spmv(const double *x, double *y, double (&dot)[4])
+    {
+        if (a.gather_cg) spmv_impl<EPI, true>(x, y, dot); else spmv_impl<EPI, false>(x, y, dot);
+    }
+    template <int EPI, bool CG>
+    __device__ void spmv_impl(const double *x, double *y, double (&dot)[4])
     {
         const int stages = a.stages, cap = a.cap;
         const int sub = tid % LANES, row_in_tile = tid / LANES;
@@ -399,7 +406,7 @@ struct Mega {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const unsigned idx = min(jj + (unsigned)(u * CT), h.hi - 1u);
-                        pv[u] = sval[idx]; px[u] = ld_coherent(x + scol[idx]);
+                        pv[u] = sval[idx]; px[u] = CG ? ld_l2(x + scol[idx]) : ld_coherent(x + scol[idx]);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
@@ -452,7 +459,7 @@ struct Mega {
                     v[u] = sval[idx];
                 }
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) xv[u] = ld_coherent(x + c[u]);
+                for (int u = 0; u < UNR; ++u) xv[u] = CG ? ld_l2(x + c[u]) : ld_coherent(x + c[u]);
 #pragma unroll
                 for (int u = 0; u < UNR; ++u)
                     if (j + u * LANES < e) acc = fma(v[u], xv[u], acc);
@@ -506,7 +513,7 @@ struct Mega {
                 }
             }
             nbar(2, RED_THREADS);
-            if (tid < 32) fence_gpu();                 // acquire (+ L1 invalidate) after ALL pollers are through
+            if (tid < 32 && !a.gather_cg) fence_gpu(); // acquire (+ L1 invalidate) after ALL pollers are through
         }
         nbar(1, CT);
         if (sh.flags[3]) { if (tid == 0) { sh.sc.error = 1; sh.sc.done = 1; } nbar(1, CT); }

@@ -62,6 +62,7 @@ struct MegaArgs {
     int cap, stages;
     int ghost_off;
     int l2_hint;                // 1: matrix stream is loaded with an L2 evict-first policy
+    int gather_cg;              // 1: SpMV gathers bypass L1 (ld.global.cg) and the neighbour waits skip the acquire fence
     double *vec_base; long long vstride;   // arena vectors: vec(id) = vec_base + id * vstride
     VecPtrs v;
     PushPlan push;

@@ -93,6 +93,7 @@ struct Seq {
         a.tile_flag = m->mega.d_tile_flag;
         a.cap = m->mega.cap; a.stages = m->mega.stages;
         a.ghost_off = m->ghost_off; a.l2_hint = c.cfg.l2_hint;
+        a.gather_cg = c.cfg.gather_cg >= 0 ? c.cfg.gather_cg : 0;
         a.vec_base = m->vec_base; a.vstride = m->vstride;
         a.v = ptrs();
         a.push.npeers = m->world > 1 ? m->npush : 0;
