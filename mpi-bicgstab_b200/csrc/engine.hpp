@@ -42,6 +42,7 @@ struct Config {
     int mega_threads = 0;        // 0 choose (512, else 256)
     int mega_trace = 0;
     int mega_lanes = 0;          // lanes per row of the persistent kernel's SpMV (0 choose from the mean row length)
+    int stage_upload = 1;        // large pageable host arrays are uploaded through multi-threaded pinned staging (Context::h2d)
     int gather_cg = -1;          // SpMV gathers of the persistent kernel through L2 only + fence-free neighbour waits (-1: default = off)
     int l2_hint = 1;             // matrix stream loaded with an L2 evict-first policy (persistent kernel)
     int row_weight = 1200;       // per-row cost (byte equivalents) next to 24 B per entry when CTA row ranges are balanced
@@ -112,6 +113,13 @@ struct Context {
     unsigned long long next_arena_id = 1;
     void release_arenas();       // collective: unmap the peers' arenas, free the parked ones
     void host_allgather(const void *send, void *recv, size_t bytes);
+    // Host -> device copy ordered on `stream`.  Pinned sources go straight to cudaMemcpyAsync.  Large PAGEABLE sources (what the
+    // reference's main.c passes: plain malloc, main.c:81-107) are staged by a few host threads through pinned bounce buffers, each
+    // thread copying and issuing its own chunks -- the driver's own pageable path stages with one thread (~11 GB/s).
+    void h2d(void *dst, const void *src, size_t bytes);
+    struct Stager { cudaStream_t st = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr}; cudaEvent_t done = nullptr; char *buf[2] = {nullptr, nullptr}; };
+    std::vector<Stager> stagers;
+    int stage_threads = 4;
 };
 Context &ctx();
 void load_config_from_env(Config &c);

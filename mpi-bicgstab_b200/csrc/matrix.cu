@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <ctime>
+#include <thread>
 
 namespace bicg {
 
@@ -54,6 +55,7 @@ int set_option(Config &c, const char *key, const char *value)
     else if (k == "MEGA_LANES") c.mega_lanes = as_int();
     else if (k == "L2_HINT") c.l2_hint = as_int();
     else if (k == "GATHER_CG") c.gather_cg = as_int();
+    else if (k == "STAGE_UPLOAD") c.stage_upload = as_int();
     else if (k == "BOUNDARY_WEIGHT") c.boundary_weight = std::max(0, as_int());
     else if (k == "ROW_WEIGHT") c.row_weight = std::max(1, as_int());
     else if (k == "DEVICE") c.device = as_int();
@@ -71,7 +73,7 @@ void load_config_from_env(Config &c)
 {
     static const char *keys[] = {"BICG_TOL", "BICG_MAX_ITER", "BICG_OUT_ITER", "BICG_QUIET", "BICG_SPMV",
                                  "BICG_SPMV_LANES", "BICG_SPMV_THREADS", "BICG_SPMV_STAGES", "BICG_SPMV_CTAS",
-                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_MEGA_LANES", "BICG_L2_HINT", "BICG_GATHER_CG", "BICG_BOUNDARY_WEIGHT", "BICG_ROW_WEIGHT", "BICG_DEVICE",
+                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_MEGA_LANES", "BICG_L2_HINT", "BICG_GATHER_CG", "BICG_STAGE_UPLOAD", "BICG_BOUNDARY_WEIGHT", "BICG_ROW_WEIGHT", "BICG_DEVICE",
                                  "BICG_HALO_GAP", "BICG_VERBOSE", "BICG_PEER_TIMEOUT_S", "BICG_SHIFT_TOL", "BICG_SHIFT_MAX_ITER", "BICG_FENCE_WRITERS"};
     for (const char *k : keys)
         if (const char *v = getenv(k)) set_option(c, k, v);
@@ -161,6 +163,63 @@ void Context::dev_release_all()
     for (auto &kv : pool) cudaFree(kv.second);
     pool.clear();
     pool_bytes = 0;
+}
+
+void Context::h2d(void *dst, const void *src, size_t bytes)
+{
+    constexpr size_t CHUNK = (size_t)8 << 20, MIN_STAGED = (size_t)16 << 20;
+    bool pageable = false;
+    if (bytes >= MIN_STAGED && cfg.stage_upload) {
+        cudaPointerAttributes at{};
+        const cudaError_t e = cudaPointerGetAttributes(&at, src);
+        if (e != cudaSuccess) (void)cudaGetLastError();
+        pageable = (e != cudaSuccess) || at.type == cudaMemoryTypeUnregistered;
+    }
+    if (!pageable) { BICG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); return; }
+    const int T = std::max(1, std::min(stage_threads, 8));
+    if ((int)stagers.size() < T) {
+        const size_t old = stagers.size();
+        stagers.resize((size_t)T);
+        for (size_t t = old; t < (size_t)T; ++t) {
+            Stager &s = stagers[t];
+            BICG_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            BICG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            for (int b = 0; b < 2; ++b) {
+                BICG_CUDA(cudaEventCreateWithFlags(&s.ev[b], cudaEventDisableTiming));
+                BICG_CUDA(cudaHostAlloc((void **)&s.buf[b], CHUNK, cudaHostAllocDefault));
+            }
+        }
+    }
+    // the staged copies run on side streams: they must start after whatever `stream` has queued for dst, and `stream` continues after them
+    cudaEvent_t start;
+    BICG_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    BICG_CUDA(cudaEventRecord(start, stream));
+    const size_t nchunks = (bytes + CHUNK - 1) / CHUNK;
+    const int dev = device;
+    std::vector<std::thread> th;
+    std::vector<int> rc((size_t)T, 0);
+    for (int t = 0; t < T; ++t) {
+        th.emplace_back([&, t] {
+            if (cudaSetDevice(dev) != cudaSuccess) { rc[(size_t)t] = 1; return; }
+            Stager &s = stagers[(size_t)t];
+            if (cudaStreamWaitEvent(s.st, start, 0) != cudaSuccess) { rc[(size_t)t] = 1; return; }
+            int b = 0;
+            for (size_t ck = (size_t)t; ck < nchunks; ck += (size_t)T, b ^= 1) {
+                const size_t off = ck * CHUNK, len = std::min(CHUNK, bytes - off);
+                if (cudaEventSynchronize(s.ev[b]) != cudaSuccess) { rc[(size_t)t] = 1; return; }      // bounce buffer free again
+                memcpy(s.buf[b], (const char *)src + off, len);
+                if (cudaMemcpyAsync((char *)dst + off, s.buf[b], len, cudaMemcpyHostToDevice, s.st) != cudaSuccess ||
+                    cudaEventRecord(s.ev[b], s.st) != cudaSuccess) { rc[(size_t)t] = 1; return; }
+            }
+            if (cudaEventRecord(s.done, s.st) != cudaSuccess) rc[(size_t)t] = 1;
+        });
+    }
+    for (auto &x : th) x.join();
+    for (int t = 0; t < T; ++t) {
+        if (rc[(size_t)t]) fatal("bicgstab_b200: staged host-to-device upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        BICG_CUDA(cudaStreamWaitEvent(stream, stagers[(size_t)t].done, 0));
+    }
+    cudaEventDestroy(start);
 }
 
 void Context::host_allgather(const void *send, void *recv, size_t bytes)
@@ -551,8 +610,8 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     BICG_CUDA(cudaMemcpyAsync(m->d_ptr, h_ptr, ((size_t)m->n_loc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
     if (!no) {
         if (nd) {
-            BICG_CUDA(cudaMemcpyAsync(m->d_val, diag->val, nd * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-            BICG_CUDA(cudaMemcpyAsync(m->d_col, diag->col, nd * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+            c.h2d(m->d_val, diag->val, nd * sizeof(double));
+            c.h2d(m->d_col, diag->col, nd * sizeof(unsigned));
         }
     } else {
         const size_t np1 = (size_t)m->n_loc + 1;
@@ -563,11 +622,11 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
         unsigned *t_ptr = (unsigned *)c.dev_alloc(2 * np1 * sizeof(unsigned));
         int *t_runs = (int *)c.dev_alloc(m->recv_runs.size() * sizeof(int));
         if (nd) {
-            BICG_CUDA(cudaMemcpyAsync(t_dval, diag->val, nd * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-            BICG_CUDA(cudaMemcpyAsync(t_dcol, diag->col, nd * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+            c.h2d(t_dval, diag->val, nd * sizeof(double));
+            c.h2d(t_dcol, diag->col, nd * sizeof(unsigned));
         }
-        BICG_CUDA(cudaMemcpyAsync(t_oval, offd->val, no * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-        BICG_CUDA(cudaMemcpyAsync(t_ocol, offd->col, no * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+        c.h2d(t_oval, offd->val, no * sizeof(double));
+        c.h2d(t_ocol, offd->col, no * sizeof(unsigned));
         BICG_CUDA(cudaMemcpyAsync(t_ptr, diag->ptr, np1 * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
         BICG_CUDA(cudaMemcpyAsync(t_ptr + np1, offd->ptr, np1 * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
         BICG_CUDA(cudaMemcpyAsync(t_runs, m->recv_runs.data(), m->recv_runs.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
