@@ -34,7 +34,7 @@ int run_reference_entry(int method, CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *i
     bicg_stats st{};
     solve(m, method, x, r, krr, nrr, 0, &st);
     const double t2 = wall();
-    st.upload_ms = fresh ? m->upload_ms : 0.0;
+    st.upload_ms = fresh ? matrix_upload_ms(m) : 0.0;
     st.h2d_bytes += fresh ? m->upload_bytes : 0;
     c.last_stats = st;
     print_reference_lines(st, c.last_hist);

@@ -9,6 +9,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <initializer_list>
 #include <map>
 #include <string>
 #include <vector>
@@ -101,6 +102,10 @@ struct Context {
     void *dev_alloc(size_t bytes);
     void  dev_free(void *p);
     void  dev_release_all();
+    void  dev_free_after(std::initializer_list<void *> ptrs, cudaEvent_t ev);   // dev_free once `ev` has completed
+    void  dev_sweep(bool wait);
+    struct Deferred { cudaEvent_t ev; std::vector<void *> ptrs; };
+    std::vector<Deferred> deferred;
     std::multimap<size_t, void *> pool;
     std::map<void *, size_t> live;
     size_t pool_bytes = 0;
@@ -206,6 +211,7 @@ struct bicg_matrix {
     const void *host_key = nullptr;
     uint64_t host_fp = 0;            // content fingerprint of the caller's arrays at upload time (matrix.cu)
     double upload_ms = 0.0;
+    cudaEvent_t ev_upload0 = nullptr, ev_upload1 = nullptr;   // around upload + planning; read lazily (matrix_upload_ms)
     uint64_t upload_bytes = 0;
 
     double *vec(int id) const { return vec_base + (long long)id * vstride; }
@@ -216,6 +222,7 @@ namespace bicg {
 // matrix.cu
 bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info);
 void matrix_destroy(bicg_matrix *m);
+double matrix_upload_ms(bicg_matrix *m);
 bicg_matrix *matrix_get_cached(const CSR_Matrix *diag, const CSR_Matrix *offd, const INFO_Matrix *info, bool *fresh);
 // solve.cu
 int  solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, int device_vectors, bicg_stats *st);

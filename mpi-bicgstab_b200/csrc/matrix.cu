@@ -123,8 +123,30 @@ void Context::ensure()
     ready = true;
 }
 
+void Context::dev_free_after(std::initializer_list<void *> ptrs, cudaEvent_t ev)
+{
+    deferred.push_back(Deferred{ev, std::vector<void *>(ptrs)});
+}
+
+// blocks whose last use has completed go back to the pool
+void Context::dev_sweep(bool wait)
+{
+    for (size_t i = 0; i < deferred.size();) {
+        const cudaError_t e = wait ? cudaEventSynchronize(deferred[i].ev) : cudaEventQuery(deferred[i].ev);
+        if (e == cudaSuccess) {
+            for (void *p : deferred[i].ptrs) dev_free(p);
+            cudaEventDestroy(deferred[i].ev);
+            deferred.erase(deferred.begin() + (long)i);
+        } else {
+            if (e != cudaErrorNotReady) (void)cudaGetLastError();
+            ++i;
+        }
+    }
+}
+
 void *Context::dev_alloc(size_t bytes)
 {
+    if (!deferred.empty()) dev_sweep(false);
     bytes = (bytes + 511) & ~(size_t)511;
     void *p = nullptr;
     auto it = pool.find(bytes);
@@ -134,8 +156,9 @@ void *Context::dev_alloc(size_t bytes)
         pool_bytes -= bytes;
     } else {
         cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess && pool_bytes) {          // give the cached blocks back and retry once
+        if (e != cudaSuccess && (pool_bytes || !deferred.empty())) {          // give the cached blocks back and retry once
             (void)cudaGetLastError();
+            dev_sweep(true);
             dev_release_all();
             e = cudaMalloc(&p, bytes);
         }
@@ -276,9 +299,9 @@ static bool build_tma_plan(const bicg_matrix *m, const unsigned *h_ptr, int lane
     out.grid = std::max(1, std::min(nt, c.sm_count * out.ctas_per_sm));
     out.d_tile_row = (decltype(out.d_tile_row))c.dev_alloc(tile_row.size() * sizeof(int));
     out.d_tile_nz = (decltype(out.d_tile_nz))c.dev_alloc(tile_nz.size() * sizeof(unsigned));
-    BICG_CUDA(cudaMemcpyAsync(out.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-    BICG_CUDA(cudaMemcpyAsync(out.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
-    BICG_CUDA(cudaStreamSynchronize(c.stream));   // the host vectors die here
+    // synchronous copies (legacy stream; c.stream is non-blocking): they do not queue behind the matrix upload on c.stream
+    BICG_CUDA(cudaMemcpy(out.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice));
+    BICG_CUDA(cudaMemcpy(out.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
     return true;
 }
 
@@ -482,14 +505,13 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::ve
         mp.d_tile_flag = nullptr;
         if (chunked) {
             mp.d_tile_flag = (int *)c.dev_alloc(tile_flag.size() * sizeof(int));
-            BICG_CUDA(cudaMemcpyAsync(mp.d_tile_flag, tile_flag.data(), tile_flag.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+            BICG_CUDA(cudaMemcpy(mp.d_tile_flag, tile_flag.data(), tile_flag.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
-        BICG_CUDA(cudaMemcpyAsync(mp.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-        BICG_CUDA(cudaMemcpyAsync(mp.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
-        BICG_CUDA(cudaMemcpyAsync(mp.d_cta_tile, cta_tile.data(), cta_tile.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-        launch_mega_dep(m->d_col, m->d_ptr, mp.d_tile_row, mp.d_cta_tile, G, m->ghost_off, mp.d_cta_dep, c.stream);
+        BICG_CUDA(cudaMemcpy(mp.d_tile_row, tile_row.data(), tile_row.size() * sizeof(int), cudaMemcpyHostToDevice));
+        BICG_CUDA(cudaMemcpy(mp.d_tile_nz, tile_nz.data(), tile_nz.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        BICG_CUDA(cudaMemcpy(mp.d_cta_tile, cta_tile.data(), cta_tile.size() * sizeof(int), cudaMemcpyHostToDevice));
+        launch_mega_dep(m->d_col, m->d_ptr, mp.d_tile_row, mp.d_cta_tile, G, m->ghost_off, mp.d_cta_dep, c.stream);   // behind the upload
         BICG_CUDA(cudaGetLastError());
-        BICG_CUDA(cudaStreamSynchronize(c.stream));     // the host vectors die here
         mp.ok = true;
         if (c.cfg.verbose)
             fprintf(stderr, "[bicg mega r%d] threads=%d lanes=%d stages=%d cap=%d tiles=%d smem=%zu\n", m->rank, threads, lanes,
@@ -600,46 +622,6 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     m->max_row = max_row;
     m->mean_row = m->n_loc ? (double)m->nnz / m->n_loc : 0.0;
 
-    const size_t pad = 16;
-    m->d_val = (decltype(m->d_val))c.dev_alloc((m->nnz + pad) * sizeof(double));
-    m->d_col = (decltype(m->d_col))c.dev_alloc((m->nnz + pad) * sizeof(unsigned));
-    m->d_ptr = (decltype(m->d_ptr))c.dev_alloc(((size_t)m->n_loc + 1 + pad) * sizeof(unsigned));
-    BICG_CUDA(cudaMemsetAsync(m->d_ptr + m->n_loc + 1, 0, pad * sizeof(unsigned), c.stream));
-    BICG_CUDA(cudaMemsetAsync(m->d_val + m->nnz, 0, pad * sizeof(double), c.stream));
-    BICG_CUDA(cudaMemsetAsync(m->d_col + m->nnz, 0, pad * sizeof(unsigned), c.stream));
-    BICG_CUDA(cudaMemcpyAsync(m->d_ptr, h_ptr, ((size_t)m->n_loc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
-    if (!no) {
-        if (nd) {
-            c.h2d(m->d_val, diag->val, nd * sizeof(double));
-            c.h2d(m->d_col, diag->col, nd * sizeof(unsigned));
-        }
-    } else {
-        const size_t np1 = (size_t)m->n_loc + 1;
-        double *t_dval = (double *)c.dev_alloc(std::max<size_t>(nd, 1) * sizeof(double));
-        double *t_oval = (double *)c.dev_alloc(no * sizeof(double));
-        unsigned *t_dcol = (unsigned *)c.dev_alloc(std::max<size_t>(nd, 1) * sizeof(unsigned));
-        unsigned *t_ocol = (unsigned *)c.dev_alloc(no * sizeof(unsigned));
-        unsigned *t_ptr = (unsigned *)c.dev_alloc(2 * np1 * sizeof(unsigned));
-        int *t_runs = (int *)c.dev_alloc(m->recv_runs.size() * sizeof(int));
-        if (nd) {
-            c.h2d(t_dval, diag->val, nd * sizeof(double));
-            c.h2d(t_dcol, diag->col, nd * sizeof(unsigned));
-        }
-        c.h2d(t_oval, offd->val, no * sizeof(double));
-        c.h2d(t_ocol, offd->col, no * sizeof(unsigned));
-        BICG_CUDA(cudaMemcpyAsync(t_ptr, diag->ptr, np1 * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
-        BICG_CUDA(cudaMemcpyAsync(t_ptr + np1, offd->ptr, np1 * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
-        BICG_CUDA(cudaMemcpyAsync(t_runs, m->recv_runs.data(), m->recv_runs.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-        const int blocks = std::max(1, std::min((m->n_loc + 255) / 256, c.sm_count * 8));
-        merge_rows_kernel<<<blocks, 256, 0, c.stream>>>(m->n_loc, t_ptr, t_ptr + np1, t_dval, t_dcol, t_oval, t_ocol, t_runs,
-                                                        (int)(m->recv_runs.size() / 4), m->ghost_off, m->d_val, m->d_col);
-        BICG_CUDA(cudaGetLastError());
-        // back to the pool: everything that re-uses these blocks is ordered behind the kernel on the same stream
-        c.dev_free(t_dval); c.dev_free(t_oval); c.dev_free(t_dcol); c.dev_free(t_ocol); c.dev_free(t_ptr); c.dev_free(t_runs);
-    }
-    m->upload_bytes = m->nnz * 12 + ((size_t)m->n_loc + 1) * 4 * (no ? 2 : 1);
-
-    lap("merge + alloc + H2D matrix");
     // ---- arena -------------------------------------------------------------------------------------
     m->hist_cap = std::max(c.cfg.max_iter, 1000) + 2;
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -684,6 +666,53 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     BICG_CUDA(cudaStreamSynchronize(c.stream));            // arena zeroed before any peer may write into it
 
     lap("arena alloc + zero");
+    // ---- upload: asynchronous from here on, so that planning and the bootstrap exchange below overlap with the copies ----
+    const size_t pad = 16;
+    m->d_val = (decltype(m->d_val))c.dev_alloc((m->nnz + pad) * sizeof(double));
+    m->d_col = (decltype(m->d_col))c.dev_alloc((m->nnz + pad) * sizeof(unsigned));
+    m->d_ptr = (decltype(m->d_ptr))c.dev_alloc(((size_t)m->n_loc + 1 + pad) * sizeof(unsigned));
+    BICG_CUDA(cudaMemsetAsync(m->d_ptr + m->n_loc + 1, 0, pad * sizeof(unsigned), c.stream));
+    BICG_CUDA(cudaMemsetAsync(m->d_val + m->nnz, 0, pad * sizeof(double), c.stream));
+    BICG_CUDA(cudaMemsetAsync(m->d_col + m->nnz, 0, pad * sizeof(unsigned), c.stream));
+    BICG_CUDA(cudaMemcpyAsync(m->d_ptr, h_ptr, ((size_t)m->n_loc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+    if (!no) {
+        if (nd) {
+            c.h2d(m->d_val, diag->val, nd * sizeof(double));
+            c.h2d(m->d_col, diag->col, nd * sizeof(unsigned));
+        }
+    } else {
+        const size_t np1 = (size_t)m->n_loc + 1;
+        double *t_dval = (double *)c.dev_alloc(std::max<size_t>(nd, 1) * sizeof(double));
+        double *t_oval = (double *)c.dev_alloc(no * sizeof(double));
+        unsigned *t_dcol = (unsigned *)c.dev_alloc(std::max<size_t>(nd, 1) * sizeof(unsigned));
+        unsigned *t_ocol = (unsigned *)c.dev_alloc(no * sizeof(unsigned));
+        unsigned *t_ptr = (unsigned *)c.dev_alloc(2 * np1 * sizeof(unsigned));
+        int *t_runs = (int *)c.dev_alloc(m->recv_runs.size() * sizeof(int));
+        // small arrays first: a cudaMemcpyAsync from pageable memory synchronises the stream before it starts, so it must not
+        // queue behind the big copies
+        BICG_CUDA(cudaMemcpyAsync(t_runs, m->recv_runs.data(), m->recv_runs.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        BICG_CUDA(cudaMemcpyAsync(t_ptr, diag->ptr, np1 * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+        BICG_CUDA(cudaMemcpyAsync(t_ptr + np1, offd->ptr, np1 * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+        if (nd) {
+            c.h2d(t_dval, diag->val, nd * sizeof(double));
+            c.h2d(t_dcol, diag->col, nd * sizeof(unsigned));
+        }
+        c.h2d(t_oval, offd->val, no * sizeof(double));
+        c.h2d(t_ocol, offd->col, no * sizeof(unsigned));
+        const int blocks = std::max(1, std::min((m->n_loc + 255) / 256, c.sm_count * 8));
+        merge_rows_kernel<<<blocks, 256, 0, c.stream>>>(m->n_loc, t_ptr, t_ptr + np1, t_dval, t_dcol, t_oval, t_ocol, t_runs,
+                                                        (int)(m->recv_runs.size() / 4), m->ghost_off, m->d_val, m->d_col);
+        BICG_CUDA(cudaGetLastError());
+        // back to the pool -- but only once the merge has run: planning below fills freshly allocated blocks with SYNCHRONOUS
+        // copies that are not ordered behind this stream
+        cudaEvent_t merged;
+        BICG_CUDA(cudaEventCreateWithFlags(&merged, cudaEventDisableTiming));
+        BICG_CUDA(cudaEventRecord(merged, c.stream));
+        c.dev_free_after({t_dval, t_oval, t_dcol, t_ocol, t_ptr, t_runs}, merged);
+    }
+    m->upload_bytes = m->nnz * 12 + ((size_t)m->n_loc + 1) * 4 * (no ? 2 : 1);
+
+    lap("merge + alloc + H2D matrix");
     // ---- peers: exchange arena handles + layouts, then the halo runs -------------------------------
     m->comm.rank = m->rank; m->comm.world = m->world;
     m->comm.timeout_ns = (unsigned long long)c.cfg.peer_timeout_s * 1000000000ull;
@@ -772,8 +801,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
         if (!m->d_ll) m->mega.ok = false;                 // the multi-GPU loops of the persistent kernel need the LL halo regions
         const int ok = m->mega.ok ? 1 : 0;
         for (int p = 0; p < m->world; ++p)
-            BICG_CUDA(cudaMemcpyAsync(&m->peer_msync[p]->st.plan_ok[m->rank], &ok, sizeof(int), cudaMemcpyDefault, c.stream));
-        BICG_CUDA(cudaStreamSynchronize(c.stream));
+            BICG_CUDA(cudaMemcpy(&m->peer_msync[p]->st.plan_ok[m->rank], &ok, sizeof(int), cudaMemcpyDefault));
     }
     if (c.cfg.mega_trace) {
         const size_t tb = ((size_t)2 * MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS + (size_t)2 * MEGA_MAX_CTAS) * sizeof(unsigned long long);
@@ -783,11 +811,7 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
 
     lap("spmv plan");
     BICG_CUDA(cudaEventRecord(ev1, c.stream));
-    BICG_CUDA(cudaEventSynchronize(ev1));
-    float ms = 0.f;
-    BICG_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    m->upload_ms = ms;
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    m->ev_upload0 = ev0; m->ev_upload1 = ev1;              // elapsed time is read after the first solve (matrix_upload_ms): no wait here
     if (m->world > 1) {          // nobody may start pushing before every rank has mapped every arena
         int token = 0; std::vector<int> all((size_t)m->world);
         c.host_allgather(&token, all.data(), sizeof(int));
@@ -798,11 +822,24 @@ bicg_matrix *matrix_create(const CSR_Matrix *diag, const CSR_Matrix *offd, const
     return m;
 }
 
+double matrix_upload_ms(bicg_matrix *m)
+{
+    if (m->ev_upload0) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(m->ev_upload1) == cudaSuccess && cudaEventElapsedTime(&ms, m->ev_upload0, m->ev_upload1) == cudaSuccess)
+            m->upload_ms = ms;
+        cudaEventDestroy(m->ev_upload0); cudaEventDestroy(m->ev_upload1);
+        m->ev_upload0 = m->ev_upload1 = nullptr;
+    }
+    return m->upload_ms;
+}
+
 void matrix_destroy(bicg_matrix *m)
 {
     if (!m) return;
     Context &c = ctx();
     if (c.ready) cudaStreamSynchronize(c.stream);
+    (void)matrix_upload_ms(m);
     for (auto it = c.cache.begin(); it != c.cache.end();) {
         if (it->second == m) it = c.cache.erase(it); else ++it;
     }
