@@ -87,12 +87,13 @@ def test_rows_longer_than_a_stage(B, O, n, long_rows, request):
         assert st["kernel_launches"] <= 8                     # ... and the loop still ran as ONE persistent kernel
     ref = O.solve("bicgstab", n, ptr, col, val, O.spmv(n, ptr, col, val, np.ones(n)), tol=1e-10, max_iter=500)
     # The dense rows sum 12 000 / 40 000 products of mixed sign: every SpMV carries a cancellation error ~1e-12 that BiCGStab
-    # amplifies quickly (measured: 2e-8 relative by iteration 3, in BOTH loop implementations), so the history is held to
-    # 1e-10 for the first two iterations only; after that convergence-level agreement.
+    # amplifies quickly (measured: 4e-10 relative at iteration 2 with three 40 000-entry rows, 2e-8 by iteration 3, in BOTH loop
+    # implementations), so the history is held to 1e-10 for the first iteration and 1e-9 for the second; after that
+    # convergence-level agreement.
     m = min(2, it, ref["iters"])
     hist = B.last_history()
     got, want = np.sqrt(hist[1:m + 1]), np.sqrt(ref["hist"][1:m + 1])
-    assert np.all(np.abs(got - want) <= 1e-10 * want + 1e-15), (got, want)
+    assert np.all(np.abs(got - want) <= np.array([1e-10, 1e-9])[:m] * want + 1e-15), (got, want)
     assert abs(it - ref["iters"]) <= max(2, int(0.05 * ref["iters"])), (it, ref["iters"])
     assert np.abs(xs - 1).max() < 1e-7
 
