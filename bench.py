@@ -484,7 +484,7 @@ def run_b200(args, w):
         spmv_obj = {"kernel": "spmv_ws_kernel + fused (r#,s) dot" if st.spmv_kind == 0 else "spmv_rowsplit_kernel + dot",
                     "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "frac": k_bytes / (k_ms * 1e-3) / 1e9 / peak, "unit": "GB/s",
                     "algorithmic_bytes_per_launch": k_bytes, "avg_launch_us": k_ms * 1e3,
-                    "traffic": read_traffic("dram_bytes_per_launch"),
+                    "traffic": read_traffic("dram_bytes_per_launch") if (world == 1 and args.workload == "transport") else None,
                     "in_per_phase_kernels": {"spmv_avg_us": 1e3 * prof_ms[0] / max(prof_cnt[0], 1),
                                              "vector_avg_us": 1e3 * prof_ms[1] / max(prof_cnt[1], 1),
                                              "spmv_share_of_step": prof_ms[0] / max(sum(prof_ms), 1e-12)}}
@@ -529,8 +529,11 @@ def run_b200(args, w):
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
-        line["roofline"]["traffic_source"] = ("profiles/spmv_traffic.json (ncu --set full dram__bytes_read + dram__bytes_write of the same kernel on the "
-                                              "same matrix, profiles/r02c_mega_kernel_ncu_full.json), not measured in this run")
+        if world == 1 and args.workload == "transport":
+            line["roofline"]["traffic_source"] = ("profiles/spmv_traffic.json (ncu --set full dram__bytes_read + dram__bytes_write of the same kernel on the "
+                                                  "same matrix, profiles/r02c_mega_kernel_ncu_full.json), not measured in this run")
+        else:
+            line["roofline"]["traffic_source"] = "no ncu capture for this workload / rank count: traffic null"
         rr = None
         if not args.no_cpu:
             try:
