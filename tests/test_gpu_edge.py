@@ -73,8 +73,8 @@ def test_rows_longer_than_a_stage(B, O, n, long_rows, request):
     multiplies cooperatively (plan.cpp / mega.cu), so the device-resident loop stays in use.  Results unchanged."""
     A = sp.lil_matrix(_ragged(n, 5, 6))
     for r in long_rows:
-        A[r, :] = -1e-3
-        A[r, r] = 0.002 * n + 10.0
+        A[r, :] = -2.0 / n                                    # the dense row weighs as much as an ordinary one: the
+        A[r, r] = 4.0                                         # system stays well conditioned (14 iterations to 1e-10)
     blk, n, ptr, col, val = _block(B, A)
     x = np.random.default_rng(4).standard_normal(n)
     assert rel_err(B.spmv_ovlap(blk, x), O.spmv(n, ptr, col, val, x, long_double=True)) <= 1e-13
@@ -86,15 +86,16 @@ def test_rows_longer_than_a_stage(B, O, n, long_rows, request):
     if "mega" in request.node.name:
         assert st["kernel_launches"] <= 8                     # ... and the loop still ran as ONE persistent kernel
     ref = O.solve("bicgstab", n, ptr, col, val, O.spmv(n, ptr, col, val, np.ones(n)), tol=1e-10, max_iter=500)
-    # The dense rows sum 12 000 / 40 000 products of mixed sign: every SpMV carries a cancellation error ~1e-12 that BiCGStab
-    # amplifies quickly (measured: 4e-10 relative at iteration 2 with three 40 000-entry rows, 2e-8 by iteration 3, in BOTH loop
-    # implementations), so the history is held to 1e-10 for the first iteration and 1e-9 for the second; after that
-    # convergence-level agreement.
-    m = min(2, it, ref["iters"])
+    # A 12 000 / 40 000-term row sum depends on the summation order at the 1e-12 level (the oracle itself moves by 1e-12 ...
+    # 3e-11 over iterations 1-4 when the entries of each row are merely stored in reverse order; iteration counts agree), so
+    # the first four history entries are held to 1e-9, then convergence-level agreement.  (A first version of this test gave
+    # the dense rows a weight of 1e-3 per entry: that system is chaotic -- 22 vs 28 iterations between the two storage orders
+    # in the oracle alone -- and says nothing about the kernel.)
+    m = min(4, it, ref["iters"])
     hist = B.last_history()
     got, want = np.sqrt(hist[1:m + 1]), np.sqrt(ref["hist"][1:m + 1])
-    assert np.all(np.abs(got - want) <= np.array([1e-10, 1e-9])[:m] * want + 1e-15), (got, want)
-    assert abs(it - ref["iters"]) <= max(2, int(0.05 * ref["iters"])), (it, ref["iters"])
+    assert np.all(np.abs(got - want) <= 1e-9 * want + 1e-15), (got, want)
+    assert abs(it - ref["iters"]) <= 2, (it, ref["iters"])
     assert np.abs(xs - 1).max() < 1e-7
 
 
