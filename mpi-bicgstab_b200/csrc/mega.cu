@@ -2,7 +2,7 @@
 //
 // Why: with the matrix split over 8 GPUs an iteration is ~13 us of memory traffic; kernel boundaries, atomics and
 // master/worker barriers cost several times that.  Here one CTA per SM stays resident for the entire solve and
-//   * owns a fixed, contiguous, work-balanced range of rows (plan.cpp: plan_cta_tiles_weighted);
+//   * owns a fixed, contiguous, work-balanced range of rows (plan.cpp: plan_cta_tiles);
 //   * runs the SpMV phases as the warp-specialised TMA pipeline of spmv.cu over its own tiles -- the producer warp
 //     never stops: while the consumers are in a vector phase or wait at a synchronisation point it is already
 //     streaming the first stages of the NEXT SpMV (the matrix never changes), with an L2 evict-first policy so that
@@ -14,9 +14,10 @@
 //
 // Synchronisation (the replacement of MPI_Iallreduce/MPI_Wait and of the grid barriers of round 1):
 //   arrive   : a CTA publishes its partial dots as self-validating LL words {generation | 32 data bits} in its own
-//              128-byte slot of the generation's ring entry -- one release fence + plain stores, no atomics;
+//              128-byte slot of the generation's ring entry -- plain stores, no atomics (a release fence only where the
+//              arrival also publishes rows that other CTAs gather next);
 //   reduce   : (1 GPU) every CTA polls all slots of the generation (160 threads, one slot each) and adds them in a
-//              fixed order; (N GPUs) only CTA 0 does that, posts the rank's sums into every rank's mailbox over
+//              fixed order; (N GPUs) only the middle CTA (the reducer) does that, posts the rank's sums into every rank's mailbox over
 //              NVLink (LL words again), and every CTA of every rank polls its own GPU's 8 mailboxes and adds them in
 //              rank order.  Critical path: one L2 round trip (+ one NVLink hop + one L2 round trip);
 //   post / complete : the same, split (MPI_Iallreduce ... SpMV ... MPI_Wait of the pipelined variants);
@@ -257,7 +258,7 @@ struct Mega {
             }
         }
     }
-    // warp 0 of CTA 0: this rank's sums -> every rank's mailbox[parity][me]
+    // warp 0 of the reducer CTA: this rank's sums -> every rank's mailbox[parity][me]
     template <int NV>
     __device__ void post_mail()
     {

@@ -398,7 +398,7 @@ int solve(bicg_matrix *m, int method, double *x, double *r, int krr, int nrr, in
             for (int k = 0; k < 10; ++k) { o += snprintf(line + o, sizeof(line) - o, " %s %.2f |", names[k], sum[k] / std::max(1, iters - 1) * 1e-3); tot += sum[k]; }
             o += snprintf(line + o, sizeof(line) - o, " total %.2f", tot / std::max(1, iters - 1) * 1e-3);
             // inside the alpha sync point: arrive (CTA sum + release fence + slot store) | all local slots seen | posted to the
-            // peers' mailboxes (CTA 0, N > 1) | every rank's sums seen
+            // peers' mailboxes (reducer = middle CTA, N > 1) | every rank's sums seen
             double sub[4] = {0};
             const int mk[5] = {1, 11, 12, 13, 14};
             for (int it = 1; it < iters; ++it) {
