@@ -287,6 +287,10 @@ class DeviceMatrix:
         lib.bicg_spmv(self.h, _vec(x_loc, self.blk.n_loc), _dptr(y))
         return y
 
+    def resident_ctas(self):
+        """CTAs of the last persistent-kernel launch that kept their matrix slice in shared memory (BICG_RESIDENT)."""
+        return int(lib.bicg_debug_resident_ctas(self.h))
+
     def spmv_time(self, reps=20):
         ms, by = C.c_double(), C.c_double()
         lib.bicg_spmv_time(self.h, reps, C.byref(ms), C.byref(by))

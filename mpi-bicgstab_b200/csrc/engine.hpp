@@ -44,6 +44,7 @@ struct Config {
     int mega_trace = 0;
     int mega_lanes = 0;          // lanes per row of the persistent kernel's SpMV (0 choose from the mean row length)
     int stage_upload = 1;        // large pageable host arrays are uploaded through multi-threaded pinned staging (Context::h2d)
+    int resident = 1;            // persistent kernel: keep a CTA's matrix slice in shared memory for the whole solve when it fits
     int gather_cg = -1;          // SpMV gathers of the persistent kernel through L2 only + fence-free neighbour waits (-1: default = off)
     int l2_hint = 1;             // matrix stream loaded with an L2 evict-first policy (persistent kernel)
     int row_weight = 1200;       // per-row cost (byte equivalents) next to 24 B per entry when CTA row ranges are balanced
@@ -144,6 +145,7 @@ struct MegaPlan {
     bool ok = false;
     int threads = 512, lanes = 1, stages = 2, cap = 0, grid = 0;
     size_t smem = 0;
+    size_t res_smem = 0;         // > 0: every CTA's slice fits into shared memory (mega_resident_bytes of the largest one)
     int ntiles = 0;
     int *d_tile_row = nullptr;
     unsigned *d_tile_nz = nullptr;

@@ -55,6 +55,7 @@ int set_option(Config &c, const char *key, const char *value)
     else if (k == "MEGA_LANES") c.mega_lanes = as_int();
     else if (k == "L2_HINT") c.l2_hint = as_int();
     else if (k == "GATHER_CG") c.gather_cg = as_int();
+    else if (k == "RESIDENT") c.resident = as_int();
     else if (k == "STAGE_UPLOAD") c.stage_upload = as_int();
     else if (k == "BOUNDARY_WEIGHT") c.boundary_weight = std::max(0, as_int());
     else if (k == "ROW_WEIGHT") c.row_weight = std::max(1, as_int());
@@ -73,7 +74,7 @@ void load_config_from_env(Config &c)
 {
     static const char *keys[] = {"BICG_TOL", "BICG_MAX_ITER", "BICG_OUT_ITER", "BICG_QUIET", "BICG_SPMV",
                                  "BICG_SPMV_LANES", "BICG_SPMV_THREADS", "BICG_SPMV_STAGES", "BICG_SPMV_CTAS",
-                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_MEGA_LANES", "BICG_L2_HINT", "BICG_GATHER_CG", "BICG_STAGE_UPLOAD", "BICG_BOUNDARY_WEIGHT", "BICG_ROW_WEIGHT", "BICG_DEVICE",
+                                 "BICG_AUTOTUNE", "BICG_GRAPH", "BICG_UNROLL", "BICG_CACHE", "BICG_MEGA", "BICG_MEGA_THREADS", "BICG_MEGA_TRACE", "BICG_MEGA_LANES", "BICG_L2_HINT", "BICG_GATHER_CG", "BICG_RESIDENT", "BICG_STAGE_UPLOAD", "BICG_BOUNDARY_WEIGHT", "BICG_ROW_WEIGHT", "BICG_DEVICE",
                                  "BICG_HALO_GAP", "BICG_VERBOSE", "BICG_PEER_TIMEOUT_S", "BICG_SHIFT_TOL", "BICG_SHIFT_MAX_ITER", "BICG_FENCE_WRITERS"};
     for (const char *k : keys)
         if (const char *v = getenv(k)) set_option(c, k, v);
@@ -495,6 +496,17 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::ve
         mp.chunked = chunked;
         mp.threads = threads; mp.lanes = lanes; mp.stages = stages; mp.cap = cap; mp.grid = G;
         mp.smem = mega_smem_bytes(cap, stages, threads, lanes);
+        // strong-scaling regime: if EVERY CTA's slice (8-byte values, 16-bit CTA-relative columns, row pointers) fits into its
+        // shared memory the kernel may keep the matrix there for the whole solve (mega.cu: resident mode)
+        mp.res_smem = 0;
+        if (lanes == 1 && !chunked) {
+            size_t need = 0;
+            for (int g = 0; g < G; ++g) {
+                const int r0 = tile_row[(size_t)cta_tile[(size_t)g]], r1 = tile_row[(size_t)cta_tile[(size_t)g + 1]];
+                need = std::max(need, mega_resident_bytes(h_ptr[r1] - h_ptr[r0], r1 - r0));
+            }
+            if (need <= (size_t)SMEM_MAX) mp.res_smem = std::max<size_t>(need, 16);
+        }
         mp.ntiles = (int)tile_row.size() - 1;
         mp.cta_row.assign((size_t)G + 1, m->n_loc);
         for (int g = 0; g <= G; ++g) mp.cta_row[(size_t)g] = tile_row[(size_t)cta_tile[(size_t)g]];
@@ -514,8 +526,8 @@ static void build_mega_plan(bicg_matrix *m, const unsigned *h_ptr, const std::ve
         BICG_CUDA(cudaGetLastError());
         mp.ok = true;
         if (c.cfg.verbose)
-            fprintf(stderr, "[bicg mega r%d] threads=%d lanes=%d stages=%d cap=%d tiles=%d smem=%zu\n", m->rank, threads, lanes,
-                    stages, cap, mp.ntiles, mp.smem);
+            fprintf(stderr, "[bicg mega r%d] threads=%d lanes=%d stages=%d cap=%d tiles=%d smem=%zu resident_smem=%zu\n", m->rank, threads, lanes,
+                    stages, cap, mp.ntiles, mp.smem, mp.res_smem);
         return;
     }
 }

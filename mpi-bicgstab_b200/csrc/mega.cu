@@ -115,6 +115,33 @@ struct MegaShared {
     volatile int flags[4];                    // [1] producer stop, [2] consumed visits, [3] a wait timed out
 };
 
+// Resident mode (MegaArgs::resident; strong scaling, e.g. T' over 8 GPUs x 148 CTAs = 20 k entries per CTA): a CTA whose whole
+// slice fits into its shared memory -- 8-byte values, columns as 16-bit offsets into the CTA's own / ghost column windows
+// (mega_dep_kernel), row pointers -- loads it ONCE per solve; its SpMV phases then touch neither L2 nor the TMA ring for
+// the matrix.  Decided per CTA, identically by the producer thread and by every consumer thread.
+struct ResidentPlan { bool on; int row_lo, rows; unsigned nz_lo, nnz, ospan; int obase, gbase; };
+__device__ __forceinline__ ResidentPlan resident_plan(const MegaArgs &a, int t0, int t1, int lanes)
+{
+    ResidentPlan p;
+    p.on = false; p.row_lo = 0; p.rows = 0; p.nz_lo = 0u; p.nnz = 0u; p.ospan = 0u; p.obase = 0; p.gbase = 0;
+    if (!a.resident || lanes != 1 || t1 <= t0 || a.tile_flag != nullptr) return p;
+    p.row_lo = a.tile_row[t0];
+    p.rows = a.tile_row[t1] - p.row_lo;
+    if (p.rows <= 0) return p;
+    p.nz_lo = a.ptr[p.row_lo];
+    p.nnz = a.ptr[p.row_lo + p.rows] - p.nz_lo;
+    if (mega_resident_bytes(p.nnz, p.rows) > (size_t)a.smem_bytes) return p;
+    const int4 dep = a.cta_dep[blockIdx.x];
+    const bool own = dep.x <= dep.y, gh = dep.z <= dep.w;
+    p.ospan = own ? (unsigned)(dep.y - dep.x + 1) : 0u;
+    const unsigned gspan = gh ? (unsigned)(dep.w - dep.z + 1) : 0u;
+    if (p.ospan + gspan > 65536u) return p;             // the columns of this CTA do not fit 16-bit offsets: it streams
+    p.obase = own ? dep.x : 0;
+    p.gbase = a.ghost_off + (gh ? dep.z : 0) - (int)p.ospan;   // column = gbase + code for codes >= ospan
+    p.on = true;
+    return p;
+}
+
 template <int CT, int LANES>
 struct Mega {
     static constexpr int RPT = CT / LANES, PROW = RPT + PROW_PAD, NCW = CT / 32, UNR = (LANES == 1) ? 16 : 8;
@@ -137,6 +164,9 @@ struct Mega {
     bool is_reducer;              // N > 1: the CTA that adds up this GPU's slots and posts them to the peers' mailboxes
     size_t stage_bytes;
     int trace_it, trace_who;
+    bool resident;                // this CTA keeps its matrix slice in shared memory (ResidentPlan)
+    ResidentPlan rp;
+    const double *rs_val; const unsigned short *rs_col; const unsigned *rs_ptr;
 
     __device__ Mega(const MegaArgs &args, MegaShared &s) : a(args), sh(s) {}
 
@@ -382,8 +412,67 @@ struct Mega {
     template <int EPI>
     __device__ void spmv(const double *x, double *y, double (&dot)[4])
     {
+        if constexpr (LANES == 1) {
+            if (resident) {
+                if (a.gather_cg) spmv_res<EPI, true>(x, y, dot); else spmv_res<EPI, false>(x, y, dot);
+                return;
+            }
+        }
         if (a.gather_cg) spmv_impl<EPI, true>(x, y, dot); else spmv_impl<EPI, false>(x, y, dot);
     }
+    // one row's epilogue: y and the dots fused into the SpMV (same operations, same order as the streaming path)
+    template <int EPI>
+    __device__ __forceinline__ void row_done(int row, double acc, double e0, double e1, double e2, double e3, double *y, double (&dot)[4])
+    {
+        y[row] = acc;
+        if (EPI == EPI_RH_Y) dot[0] = fma(e0, acc, dot[0]);
+        if (EPI == EPI_QY_YY) { dot[0] = fma(e0, acc, dot[0]); dot[1] = fma(acc, acc, dot[1]); }
+        if (EPI == EPI_CA4) {
+            dot[0] = fma(e0, e1, dot[0]); dot[1] = fma(e0, acc, dot[1]);
+            dot[2] = fma(e0, e2, dot[2]); dot[3] = fma(e0, e3, dot[3]);
+        }
+    }
+    // SpMV over a shared-memory-resident slice: thread-per-row (rows tid + k CT, so neighbouring threads gather neighbouring
+    // columns); a row's entries are accumulated in storage order, like spmv_impl.  Loads are unconditional on clamped indices
+    // (always a valid entry of this slice; no predicate per load, so the U gathers of a pass are in flight together), only the
+    // multiply-adds are guarded.
+    template <int EPI, bool CG>
+    __device__ void spmv_res(const double *x, double *y, double (&dot)[4])
+    {
+        constexpr int U = 16;
+        const double *xo = x + rp.obase, *xg = x + rp.gbase;
+        const unsigned ospan = rp.ospan;
+        const int rows = rp.rows;
+        const bool empty = rp.nnz == 0u;                      // a slice of empty rows: y = 0, the dots see acc = 0
+        const unsigned last = empty ? 0u : rp.nnz - 1u;
+        for (int r = tid; r < rows; r += CT) {
+            const int row = rp.row_lo + r;
+            unsigned j = rs_ptr[r];
+            const unsigned e = rs_ptr[r + 1];
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;     // epilogue operands: in flight during the gathers
+            if (EPI == EPI_RH_Y) e0 = a.v.rh[row];
+            if (EPI == EPI_QY_YY) e0 = a.v.r[row];
+            if (EPI == EPI_CA4) { e0 = a.v.rh[row]; e1 = a.v.r[row]; e2 = a.v.s[row]; e3 = a.v.z[row]; }
+            double acc = 0.0;
+            while (j < e) {                                    // never entered when the slice is empty
+                double xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned c = rs_col[min(min(j + (unsigned)u, e - 1u), last)];
+                    const double *src = (c < ospan ? xo : xg) + c;
+                    xv[u] = CG ? ld_l2(src) : ld_coherent(src);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {                  // the values come from shared memory when they are needed
+                    const double v = rs_val[min(min(j + (unsigned)u, e - 1u), last)];
+                    if (j + (unsigned)u < e) acc = fma(v, xv[u], acc);
+                }
+                j += (unsigned)U;
+            }
+            row_done<EPI>(row, acc, e0, e1, e2, e3, y, dot);
+        }
+    }
+
     template <int EPI, bool CG>
     __device__ void spmv_impl(const double *x, double *y, double (&dot)[4])
     {
@@ -793,7 +882,7 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
 
     if (tid >= CT) {
         // ============================ producer warp: streams this CTA's tiles round and round ==============
-        if (tid == CT && my_tiles > 0) {
+        if (tid == CT && my_tiles > 0 && !resident_plan(a, t0, t1, LANES).on) {
             volatile int *flags = sh.flags;
             const unsigned long long pol = l2_evict_first_policy();
             const bool hint = a.l2_hint != 0;
@@ -879,6 +968,24 @@ __global__ void __launch_bounds__(CT + 32, 1) bicg_mega_kernel(const __grid_cons
                 pd.runs[0] = a.push.runs[s]; pd.nruns[0] = a.push.nruns[s];
                 if (m.row_hi > m.row_lo && push_touches(pd, m.row_lo, m.row_hi)) m.push_slots |= 1u << s;
             }
+        }
+        // resident mode: the slice goes into shared memory once (plain coalesced loads; the ring is not used by this CTA)
+        m.rp = resident_plan(a, t0, t1, LANES);
+        m.resident = m.rp.on;
+        if (m.resident) {
+            const size_t nnzp = ((size_t)m.rp.nnz + 7u) & ~(size_t)7u;
+            double *sv = reinterpret_cast<double *>(dyn_smem);
+            unsigned short *sc16 = reinterpret_cast<unsigned short *>(sv + nnzp);
+            unsigned *sp = reinterpret_cast<unsigned *>(sc16 + nnzp);
+            const int gh0 = a.ghost_off + (dep.z <= dep.w ? dep.z : 0);
+            for (unsigned i = (unsigned)tid; i < m.rp.nnz; i += (unsigned)CT) {
+                sv[i] = a.val[m.rp.nz_lo + i];
+                const int cc = (int)a.col[m.rp.nz_lo + i];
+                sc16[i] = (unsigned short)(cc < a.ghost_off ? cc - m.rp.obase : cc - gh0 + (int)m.rp.ospan);
+            }
+            for (int r = tid; r <= m.rp.rows; r += CT) sp[r] = a.ptr[m.rp.row_lo + r] - m.rp.nz_lo;
+            m.rs_val = sv; m.rs_col = sc16; m.rs_ptr = sp;
+            if (tid == 0) atomicAdd(&a.sync->st.resident_ctas, 1);
         }
         nbar(1, CT);
         if (a.comm.world > 1 && (m.reads_ghost || m.gs_hi > m.gs_lo)) {

@@ -20,6 +20,7 @@ struct alignas(128) MegaState {
     unsigned red_epoch;                 // last cross-GPU reduction posted
     unsigned long long halo_epoch;      // last halo exchange signalled
     int plan_ok[MAX_RANKS];             // written by rank p at plan time: its persistent-kernel plan is usable
+    int resident_ctas;                  // CTAs of the last launch that kept their matrix slice in shared memory (test / trace aid)
 };
 
 // Lives in the IPC-shared arena: `mail` and `st.plan_ok` are written by the peers.
@@ -63,6 +64,10 @@ struct MegaArgs {
     int ghost_off;
     int l2_hint;                // 1: matrix stream is loaded with an L2 evict-first policy
     int gather_cg;              // 1: SpMV gathers bypass L1 (ld.global.cg) and the neighbour waits skip the acquire fence
+    int resident;               // 1: a CTA whose whole matrix slice fits into its shared memory (strong scaling: 8 GPUs x 148 CTAs)
+                                //    loads it ONCE per solve (values + 16-bit CTA-relative columns + row pointers) instead of streaming it
+                                //    through the TMA ring in every SpMV
+    int smem_bytes;             // dynamic shared memory of this launch
     double *vec_base; long long vstride;   // arena vectors: vec(id) = vec_base + id * vstride
     VecPtrs v;
     PushPlan push;
@@ -79,6 +84,12 @@ int    launch_mega(int threads, int lanes, int grid, size_t smem, const MegaArgs
 int    mega_setup_attributes();
 bool   mega_has_variant(int threads, int lanes);
 size_t mega_smem_bytes(int cap, int stages, int threads, int lanes);
+// shared memory a CTA needs to keep `nnz` entries of `rows` rows resident (host and device use the same formula)
+__host__ __device__ inline size_t mega_resident_bytes(unsigned nnz, int rows)
+{
+    const size_t nnzp = ((size_t)nnz + 7u) & ~(size_t)7u;
+    return nnzp * 10u + ((size_t)rows + 1u) * 4u;
+}
 // per-CTA column ranges of the plan (one launch at plan time)
 void   launch_mega_dep(const unsigned *col, const unsigned *ptr, const int *tile_row, const int *cta_tile, int grid,
                        int ghost_off, int4 *dep, cudaStream_t st);

@@ -94,6 +94,10 @@ struct Seq {
         a.cap = m->mega.cap; a.stages = m->mega.stages;
         a.ghost_off = m->ghost_off; a.l2_hint = c.cfg.l2_hint;
         a.gather_cg = c.cfg.gather_cg >= 0 ? c.cfg.gather_cg : 0;
+        size_t smem = m->mega.smem;
+        a.resident = (c.cfg.resident && m->mega.res_smem) ? 1 : 0;
+        if (a.resident) smem = std::max(smem, m->mega.res_smem);
+        a.smem_bytes = (int)smem;
         a.vec_base = m->vec_base; a.vstride = m->vstride;
         a.v = ptrs();
         a.push.npeers = m->world > 1 ? m->npush : 0;
@@ -110,7 +114,8 @@ struct Seq {
         a.trace = m->d_trace;
         a.snap = m->d_trace ? m->d_trace + (size_t)2 * MEGA_TRACE_ITERS * MEGA_TRACE_SLOTS : nullptr;
         a.snap_iter = 50;
-        int rc = launch_mega(m->mega.threads, m->mega.lanes, m->mega.grid, m->mega.smem, a, c.stream);
+        BICG_CUDA(cudaMemsetAsync(&m->d_msync->st.resident_ctas, 0, sizeof(int), c.stream));
+        int rc = launch_mega(m->mega.threads, m->mega.lanes, m->mega.grid, smem, a, c.stream);
         if (rc) {
             // e.g. the grid cannot be co-resident because something else holds SMs.  Single rank: not an error, the
             // kernel-per-phase path below does the same job.  With peers the ranks must agree on the loop
@@ -598,6 +603,17 @@ extern "C" int bicg_debug_get_scalars(bicg_matrix *m, double out[13])
     const double v[13] = {hs.rTr, hs.rTr_old, hs.rTs, hs.rTy, hs.yTy, hs.rTw, hs.wTw, hs.rTz, hs.dot_r, hs.dot_zero, hs.alpha, hs.beta, hs.omega};
     for (int k = 0; k < 13; ++k) out[k] = v[k];
     return 0;
+}
+
+extern "C" int bicg_debug_resident_ctas(bicg_matrix *m)
+{
+    using namespace bicg;
+    Context &c = ctx();
+    c.ensure();
+    int n = 0;
+    BICG_CUDA(cudaMemcpyAsync(&n, &m->d_msync->st.resident_ctas, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    BICG_CUDA(cudaStreamSynchronize(c.stream));
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------------
