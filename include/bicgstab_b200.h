@@ -78,6 +78,14 @@ int pipe_bicgstab_rr(CSR_Matrix *A_loc_diag, CSR_Matrix *A_loc_offd, INFO_Matrix
 int shifted_lopbicg_switching(CSR_Matrix *A_loc_diag, CSR_Matrix *A_loc_offd, INFO_Matrix *A_info, double *x_loc_set,
                               double *r_loc, double *sigma, int sigma_len, int seed);
 
+/* vector.h:4-7 (vector.c:3-27) on HOST arrays: the shifted drivers build and copy their right-hand sides with these
+ * (main_shifted.c:114-135, main_repeat.c:121, main_seed_diff.c:118-121), so they are exported for those programs to link
+ * unchanged (csrc/hostvec.cpp).  The solvers do not use them: their vector work is fused into the device kernels. */
+void    my_daxpy(int n, double alpha, const double *x, double *y);
+double  my_ddot(int n, const double *x, const double *y);
+void    my_dscal(int n, double alpha, double *x);
+void    my_dcopy(int n, const double *x, double *y);
+
 /* ------------------------------------------------------------------------------------------------
  * Part 2 -- extensions
  * ---------------------------------------------------------------------------------------------- */

@@ -45,6 +45,11 @@ SYMBOLS = {
     "pipe_bicgstab": (C.c_int, [_P(CSR_Matrix), _P(CSR_Matrix), _P(INFO_Matrix), C.c_void_p, C.c_void_p]),
     "pipe_bicgstab_rr": (C.c_int, [_P(CSR_Matrix), _P(CSR_Matrix), _P(INFO_Matrix), C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "shifted_lopbicg_switching": (C.c_int, [_P(CSR_Matrix), _P(CSR_Matrix), _P(INFO_Matrix), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    # vector.h:4-7 on host arrays (csrc/hostvec.cpp): what the shifted drivers prepare their right-hand sides with
+    "my_daxpy": (None, [C.c_int, C.c_double, _P(C.c_double), _P(C.c_double)]),
+    "my_ddot": (C.c_double, [C.c_int, _P(C.c_double), _P(C.c_double)]),
+    "my_dscal": (None, [C.c_int, C.c_double, _P(C.c_double)]),
+    "my_dcopy": (None, [C.c_int, _P(C.c_double), _P(C.c_double)]),
     # Part 2 -- extensions
     "bicg_abi_version": (C.c_int, []),
     "bicg_set_option": (C.c_int, [C.c_char_p, C.c_char_p]),

@@ -158,6 +158,41 @@ def test_reference_main_c_links_against_the_library(B, tmp_path):
         assert re.search(r"\bU %s\b" % sym, undefined), sym
 
 
+@pytest.mark.parametrize("driver,solver", [("main_shifted.c", "shifted_lopbicg_switching"), ("main_repeat.c", "shifted_lopbicg_switching"),
+                                           ("main_seed_diff.c", "shifted_lopbicg_switching")])
+def test_reference_shifted_drivers_link_against_the_library(B, tmp_path, driver, solver):
+    """The shifted drivers (what the reference's top-level Makefile builds), UNCHANGED: besides the loader / SpMV / solver
+    entry points they call vector.h's my_daxpy / my_dcopy on host arrays (main_shifted.c:114-135), which the library exports."""
+    src = "/root/reference/src/" + driver
+    if not os.path.exists(src):
+        pytest.skip("/root/reference not present")
+    exe = tmp_path / "shifted"
+    cmd = ["gcc", "-O2", "-w", "-I" + os.path.join(ROOT, "include", "compat"), "-I/root/reference/src", src,
+           "-L" + os.path.dirname(B.LIB_PATH), "-lbicgstab_b200", "-Wl,-rpath," + os.path.dirname(B.LIB_PATH), "-lm", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    undefined = subprocess.run(["nm", "-u", str(exe)], capture_output=True, text=True).stdout
+    for sym in (solver, "MPI_csr_spmv_ovlap", "MPI_csr_load_matrix_block", "csr_init_matrix", "my_daxpy"):
+        assert re.search(r"\bU %s\b" % sym, undefined), sym
+
+
+def test_host_blas1_entry_points_match_the_oracle_bitwise(B, O):
+    """vector.c:3-27 as exported for the drivers (csrc/hostvec.cpp) against the oracle's restatement: same loops, no contraction."""
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 1000, 4097):
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        y1, y2 = y.copy(), y.copy()
+        B.lib.my_daxpy(n, 0.37, dp(x), dp(y1)); O.daxpy(0.37, x, y2)
+        assert np.array_equal(y1, y2)
+        assert B.lib.my_ddot(n, dp(x), dp(y)) == O.ddot(x, y)
+        x1, x2 = x.copy(), x.copy()
+        B.lib.my_dscal(n, -1.25, dp(x1)); O.dscal(-1.25, x2)
+        assert np.array_equal(x1, x2)
+        z = np.empty(n)
+        B.lib.my_dcopy(n, dp(x), dp(z))
+        assert np.array_equal(z, x)
+
+
 def test_halo_runs_gap_merging(B):
     """plan_halo_runs: gap = 0 gives exactly the referenced columns, a larger gap merges runs and never loses one."""
     blk = B.gen_block("random", 4000, 6, rank=1, world=4)
