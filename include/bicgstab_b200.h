@@ -50,6 +50,8 @@ typedef struct {
 /* matrix.h:44-45 (matrix.c:188-204) */
 void csr_init_matrix(CSR_Matrix *m);
 void csr_free_matrix(CSR_Matrix *m);
+/* matrix.h:57 (matrix.c:536-551): A_diag += sigma I in place on the caller's host arrays; drops the cached device copy */
+void csr_shift_diagonal(CSR_Matrix *A_diag, double sigma);
 
 /* matrix.h:50 (matrix.c:402-419): Matrix-Market file -> this rank's diag / offd CSR blocks + partition */
 void MPI_csr_load_matrix_block(char *filename, CSR_Matrix *matrix_loc_diag, CSR_Matrix *matrix_loc_offd,
@@ -77,6 +79,10 @@ int pipe_bicgstab_rr(CSR_Matrix *A_loc_diag, CSR_Matrix *A_loc_offd, INFO_Matrix
  * BICG_SHIFT_MAX_ITER.  Not needed by main.c; it is what main_shifted.c / main_repeat.c call. */
 int shifted_lopbicg_switching(CSR_Matrix *A_loc_diag, CSR_Matrix *A_loc_offd, INFO_Matrix *A_info, double *x_loc_set,
                               double *r_loc, double *sigma, int sigma_len, int seed);
+/* shifted_switching_solver.h:13 (shifted_switching_solver.c:611): the same solve without communication overlap in the reference --
+ * identical arithmetic, so the same function here. */
+int shifted_lopbicg_switching_noovlp(CSR_Matrix *A_loc_diag, CSR_Matrix *A_loc_offd, INFO_Matrix *A_info, double *x_loc_set,
+                                     double *r_loc, double *sigma, int sigma_len, int seed);
 
 /* vector.h:4-7 (vector.c:3-27) on HOST arrays: the shifted drivers build and copy their right-hand sides with these
  * (main_shifted.c:114-135, main_repeat.c:121, main_seed_diff.c:118-121), so they are exported for those programs to link

@@ -83,6 +83,16 @@ int shifted_lopbicg_switching(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, d
     return k;
 }
 
+// shifted_switching_solver.c:611 -- the reference's twin of the function above with the halo exchange NOT overlapped with the
+// diagonal block's SpMV and per-section timers; the arithmetic is the same (x, r, residual history and return value of the two
+// compiled reference functions are bit-identical on the golden cases: tests/test_oracle_golden.py), and "overlapped or not" has
+// no counterpart here, so it is the same solve.
+int shifted_lopbicg_switching_noovlp(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_loc_set, double *r_loc, double *sigma,
+                                     int sigma_len, int seed)
+{
+    return shifted_lopbicg_switching(D, O, info, x_loc_set, r_loc, sigma, sigma_len, seed);
+}
+
 void MPI_csr_spmv_ovlap(CSR_Matrix *D, CSR_Matrix *O, INFO_Matrix *info, double *x_loc, double *x, double *y_loc)
 {
     Context &c = ctx();

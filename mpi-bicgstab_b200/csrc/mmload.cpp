@@ -38,6 +38,24 @@ extern "C" void csr_free_matrix(CSR_Matrix *m)          // matrix.c:195-204
     csr_init_matrix(m);
 }
 
+// matrix.c:536-551: add sigma to every diagonal entry of the local diagonal block, in place, on the caller's HOST arrays
+// (A + sigma I for the caller who solves the shifted systems one by one; main_shifted.c:132 keeps the call commented out).
+// A row without a stored diagonal entry is an error, as in the reference.  The cached device copy keyed by these arrays is
+// dropped explicitly (the content fingerprint would notice the change too).
+extern "C" void csr_shift_diagonal(CSR_Matrix *A_diag, double sigma)
+{
+    for (unsigned i = 0; i < A_diag->rows; ++i) {
+        bool found = false;
+        for (unsigned j = A_diag->ptr[i]; j < A_diag->ptr[i + 1] && !found; ++j)
+            if (A_diag->col[j] == i) { A_diag->val[j] += sigma; found = true; }
+        if (!found) {
+            fprintf(stderr, "Error: Diagonal element not found in row %u.\n", i);
+            exit(EXIT_FAILURE);
+        }
+    }
+    bicg_matrix_invalidate(A_diag);
+}
+
 namespace {
 
 [[noreturn]] void fail(const char *msg)

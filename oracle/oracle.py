@@ -207,8 +207,9 @@ def shifted_solve(n, ptr, col, val, b, sigma, seed, P=1, tol=1e-12, max_iter=100
     return {"ret": ret, "iters": ret - 1, "x": x, "r": r, "hist": hist[:ret], "seed": seed_out.value, "stop_iter": np.array(stop_iter[:])}
 
 
-def ref_shifted_solve(n, ptr, col, val, b, sigma, seed, tol=1e-12, max_iter=1000, flavour="strict"):
-    """The reference's own shifted_lopbicg_switching() (P = 1) called in-process on an in-memory CSR."""
+def ref_shifted_solve(n, ptr, col, val, b, sigma, seed, tol=1e-12, max_iter=1000, flavour="strict", variant="shifted_lopbicg_switching"):
+    """The reference's own shifted_lopbicg_switching() (or its _noovlp twin, shifted_switching_solver.c:611) at P = 1, called
+    in-process on an in-memory CSR."""
     L = ref_lib(flavour)
     ptr, col, val = _csr(ptr, col, val)
     sigma = np.ascontiguousarray(sigma, dtype=np.float64)
@@ -227,8 +228,9 @@ def ref_shifted_solve(n, ptr, col, val, b, sigma, seed, tol=1e-12, max_iter=1000
     r = np.array(b, dtype=np.float64)
     L.orc_ref_config(tol, max_iter, 1, 1)
     L.orc_ref_hist_reset()
-    L.shifted_lopbicg_switching.restype = C.c_int
-    ret = L.shifted_lopbicg_switching(C.byref(D), C.byref(O), C.byref(info), _p(x, _dp), _p(r, _dp), _p(sigma, _dp), int(sigma.size), int(seed))
+    fn = getattr(L, variant)
+    fn.restype = C.c_int
+    ret = fn(C.byref(D), C.byref(O), C.byref(info), _p(x, _dp), _p(r, _dp), _p(sigma, _dp), int(sigma.size), int(seed))
     cnt = L.orc_ref_hist_count()
     res = np.array([L.orc_ref_hist_res(i) for i in range(cnt)])
     return {"ret": ret, "iters": ret - 1, "x": x, "r": r, "res": res}

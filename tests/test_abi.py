@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -191,6 +192,40 @@ def test_host_blas1_entry_points_match_the_oracle_bitwise(B, O):
         z = np.empty(n)
         B.lib.my_dcopy(n, dp(x), dp(z))
         assert np.array_equal(z, x)
+
+
+def test_csr_shift_diagonal_matches_the_reference(B, O):
+    """matrix.h's csr_shift_diagonal (matrix.c:536-551) on host arrays: same values as the reference's own compiled function
+    (when oracle/_ref is there) and as the definition, a missing diagonal is fatal, and the cached device copy keyed by the
+    arrays is forgotten (no GPU needed: nothing is cached here)."""
+    blk = B.gen_block("convdiff", 12, 1.5)
+    n = blk.n
+    before = np.array(blk.diag_arrays()[0][:int(blk.diag.nz)], dtype=np.float64)
+    col = np.array(blk.diag_arrays()[1][:int(blk.diag.nz)], dtype=np.int64)
+    ptr = np.array(blk.diag_arrays()[2][:n + 1], dtype=np.int64)
+    want = before.copy()
+    rows = np.repeat(np.arange(n), np.diff(ptr))
+    want[col == rows] += 0.37
+    if O.have_ref("libref_strict.so"):
+        import ctypes
+        L = O.ref_lib("strict")
+        v2 = before.copy()
+        c2, p2 = col.astype(np.uint32), ptr.astype(np.uint32)
+        D = O._RefCSR()
+        D.val, D.col, D.ptr = O._p(v2, O._dp), O._p(c2, O._up), O._p(p2, O._up)
+        D.nz, D.rows, D.cols = int(ptr[-1]), n, n
+        L.csr_shift_diagonal.argtypes = [ctypes.POINTER(O._RefCSR), ctypes.c_double]
+        L.csr_shift_diagonal(ctypes.byref(D), 0.37)
+        assert np.array_equal(v2, want)
+    B.lib.csr_shift_diagonal(C.byref(blk.diag), 0.37)
+    got = np.array(blk.diag_arrays()[0][:int(blk.diag.nz)], dtype=np.float64)
+    assert np.array_equal(got, want) and not np.array_equal(got, before)
+    # a row without a stored diagonal entry: message + exit(EXIT_FAILURE), like the reference
+    code = ("import numpy as np, ctypes as C, mpi_bicgstab_b200 as B\n"
+            "blk = B.blocks_from_csr(3, [0, 1, 2, 3], [0, 2, 2], [1.0, 2.0, 3.0])\n"
+            "B.lib.csr_shift_diagonal(C.byref(blk.diag), 1.0)\nprint('RETURNED')\n")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert p.returncode == 1 and "RETURNED" not in p.stdout and "Diagonal element not found in row 1" in p.stderr
 
 
 def test_halo_runs_gap_merging(B):

@@ -121,3 +121,18 @@ def test_shifted_oracle_against_compiled_reference_live(B, O):
     o = O.shifted_solve(n, ptr, col, val, b, sigma, seed)
     r = O.ref_shifted_solve(n, ptr, col, val, b, sigma, seed)
     assert o["ret"] == r["ret"] and np.array_equal(o["x"], r["x"]) and np.array_equal(o["r"], r["r"])
+
+
+@pytest.mark.parametrize("name,kind,g,p0,L,scale,seed", SHIFTED_CASES)
+def test_reference_noovlp_twin_is_the_same_solve(B, O, name, kind, g, p0, L, scale, seed):
+    """shifted_lopbicg_switching_noovlp (shifted_switching_solver.c:611) differs from shifted_lopbicg_switching only in when it waits
+    for the halo exchange and in its timers: return value, every x_j, r and the residual history of the two compiled reference
+    functions are bit-identical -- which is why the library exports the former as the latter (csrc/abi.cu)."""
+    if not O.have_ref("libref_strict.so"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    blk, n, ptr, col, val = global_csr(B, kind, g, p0)
+    sigma, b = shifted_problem(O, n, ptr, col, val, L, scale, seed)
+    a = O.ref_shifted_solve(n, ptr, col, val, b, sigma, seed)
+    c = O.ref_shifted_solve(n, ptr, col, val, b, sigma, seed, variant="shifted_lopbicg_switching_noovlp")
+    assert a["ret"] == c["ret"] and np.array_equal(a["x"], c["x"]) and np.array_equal(a["r"], c["r"])
+    assert np.array_equal(a["res"], c["res"])
