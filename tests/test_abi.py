@@ -176,6 +176,25 @@ def test_reference_shifted_drivers_link_against_the_library(B, tmp_path, driver,
         assert re.search(r"\bU %s\b" % sym, undefined), sym
 
 
+def test_unchanged_shifted_driver_reaches_the_library_and_fails_loudly_without_a_gpu(B, tmp_path):
+    """main_shifted.c built against the library, run on a small Matrix-Market file: the loader (host code) works, the first
+    device call (MPI_csr_spmv_ovlap, main_shifted.c:113) must refuse to run without a GPU -- message + exit(1), no CPU path."""
+    src = "/root/reference/src/main_shifted.c"
+    if not os.path.exists(src):
+        pytest.skip("/root/reference not present")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible: the driver would really run (covered by the -m gpu tests of its library calls)")
+    exe = tmp_path / "shifted"
+    subprocess.run(["gcc", "-O2", "-w", "-I" + os.path.join(ROOT, "include", "compat"), "-I/root/reference/src", src,
+                    "-L" + os.path.dirname(B.LIB_PATH), "-lbicgstab_b200", "-Wl,-rpath," + os.path.dirname(B.LIB_PATH), "-lm",
+                    "-o", str(exe)], check=True)
+    mtx = tmp_path / "a.mtx"
+    mtx.write_text("%%MatrixMarket matrix coordinate real general\n3 3 5\n1 1 4.0\n2 2 4.0\n3 3 4.0\n1 2 -1.0\n3 2 -1.0\n")
+    p = subprocess.run([str(exe), str(mtx)], capture_output=True, text=True)
+    assert p.returncode == 1 and "IO time" in p.stdout and "no usable CUDA device" in p.stderr
+
+
 def test_host_blas1_entry_points_match_the_oracle_bitwise(B, O):
     """vector.c:3-27 as exported for the drivers (csrc/hostvec.cpp) against the oracle's restatement: same loops, no contraction."""
     rng = np.random.default_rng(5)
